@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the transport-map hot path (BASELINE.json metric: day-pair tmaps/s and Sinkhorn
+iterations/s at 1/2/4/8 B200, fraction of the HBM roofline).
+
+Workload (config.workload): BASELINE.json configs[1], the reprogramming-atlas-shaped
+compute_all_transport_maps: 39 day-pairs, 5-20k cells per day (seed 1), 30 local-PCA coordinates,
+defaults eps=0.05 lambda1=1 lambda2=50, growth_iters=3.  A STEP is one day-pair transport map:
+median-normalised cost + 3 cold-start duality-gap solves + coupling and growth row sums.  Steps walk the
+39 pairs in order; with N GPUs rank r takes pair (step*N + r) mod 39 ("independent day-pairs shard one
+per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.
+
+  value  tmaps/s with the pair's coordinates already in HBM, timed with CUDA events on the library's
+         stream, max over ranks.
+  e2e    the same through the host-buffer C-ABI call (wotb_transport_map_from_coords_host): coordinates
+         copied from pinned host memory, the float64 coupling, growth rows and potentials copied back.
+  roofline  stored-K matvec kernels (k_row / k_col), HBM-bound: algorithmic bytes = I*ld*4 per launch.
+  cpu_baseline  the float64 NumPy port of the reference (oracle/) on a bounded sample, host cores.
+
+`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the GPU
+box; oracle/ is its line-by-line restatement, pinned to the reference by tests/golden).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULTS = dict(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tolerance=1e-8, max_iter=1e7,
+                batch_size=5, scaling_iter=3000, extra_iter=1000, inner_iter_max=50)
+GROWTH_ITERS = 3
+D = 30
+WORKLOAD = "atlas-shaped compute_all_transport_maps: 39 day-pairs, 5-20k cells/day, d=30, growth_iters=3"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=39)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink every day by this factor (debugging)")
+    ap.add_argument("--kernel", default="stored", choices=["stored", "online"])
+    ap.add_argument("--cpu-cells", type=int, default=2200, help="cells/day of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port of the reference (oracle/) -- bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(pair, cells, growth_iters=1):
+    """Full reference-port solve (dense primal/dual like the reference) of `pair` subsampled to `cells`
+    cells/day.  Returns (seconds, I, J, iters)."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    n0, n1, seed = pair
+    s = min(1.0, cells / max(n0, n1))
+    m0, m1 = max(2, int(n0 * s)), max(2, int(n1 * s))
+    x0, x1, growth = synthetic.day_pair_coords(m0, m1, d=D, seed=seed)
+    t0 = time.perf_counter()
+    cost = orc.compute_default_cost_matrix(x0, x1)
+    info = orc.SolveInfo()
+    params = dict(DEFAULTS, growth_iters=growth_iters, C=cost, G=growth.copy(), info=info, gap="dense")
+    orc.compute_transport_matrix(orc.optimal_transport_duality_gap, **params)
+    return time.perf_counter() - t0, m0, m1, info.iters
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU port on host cores.  Rank 0 alone works."""
+    if rank != 0:
+        return
+    from wot_b200 import synthetic
+    pairs = synthetic.atlas_pairs(seed=1, scale=args.scale)
+    mean_ij = float(np.mean([a * b for a, b, _ in pairs]))
+    steps = max(1, min(args.steps, 6))
+    warm = min(args.warmup, 1)
+    cells = args.cpu_cells
+    per_entry = []
+    for s in range(warm + steps):
+        sec, m0, m1, iters = cpu_reference_sample(pairs[s % len(pairs)], cells, growth_iters=1)
+        if s >= warm:
+            per_entry.append(sec / (m0 * m1))
+    # one tmap of the workload = GROWTH_ITERS cold-start solves over I*J entries (time is proportional to
+    # I*J: SURVEY.md section 6, 1.4 us per entry per solve measured from 2k^2 to 10k^2)
+    sec_per_tmap = float(np.mean(per_entry)) * mean_ij * GROWTH_ITERS
+    value = 1.0 / sec_per_tmap
+    cores = blas_threads()
+    sample = ("%d timed full solves (cost + duality-gap solver with the reference's dense primal/dual) of atlas "
+              "pairs subsampled to <=%d cells/day, growth_iters=1; seconds per matrix entry scaled to the mean "
+              "atlas pair (I*J=%.3g) x growth_iters=3" % (steps, cells, mean_ij))
+    line = {
+        "impl": "reference", "metric": "day-pair transport maps per second", "value": value, "unit": "tmaps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec_per_tmap,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "solver": "duality_gap", "eps": 0.05, "lambda1": 1, "lambda2": 50},
+        "cpu_baseline": {"value": value, "unit": "tmaps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "tmaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class DevicePair:
+    """One day-pair on the device, driven through the device-pointer C ABI."""
+
+    def __init__(self, ctx, torch, max_i, max_j):
+        from wot_b200 import _lib
+        self.ctx, self.torch, self.lib, self._lib = ctx, torch, ctx.lib, _lib
+        dev = "cuda:%d" % ctx.device
+        self.ld_max = (max_j + 31) // 32 * 32
+        self.C = torch.empty(max_i * self.ld_max, dtype=torch.float32, device=dev)
+        self.out = torch.empty(max_i * max_j, dtype=torch.float64, device=dev)
+        self.x0 = torch.empty(max_i * D, dtype=torch.float64, device=dev)
+        self.x1 = torch.empty(max_j * D, dtype=torch.float64, device=dev)
+        self.G = torch.empty(max_i, dtype=torch.float64, device=dev)
+        self.f = torch.empty(max_i, dtype=torch.float64, device=dev)
+        self.g = torch.empty(max_j, dtype=torch.float64, device=dev)
+        self.rows = torch.empty(max_i, dtype=torch.float64, device=dev)
+
+    def load(self, x0, x1, growth):
+        t = self.torch
+        self.I, self.J = x0.shape[0], x1.shape[0]
+        self.x0[:x0.size].copy_(t.from_numpy(x0.ravel()))
+        self.x1[:x1.size].copy_(t.from_numpy(x1.ravel()))
+        self.G0 = t.from_numpy(growth).to(self.G.device)
+        t.cuda.synchronize()
+
+    def run(self, prm):
+        """cost + median + growth loop + coupling, inputs and outputs in HBM.  Returns per-solve infos."""
+        lib, h, L = self.lib, self.ctx.handle, self._lib
+        I, J = self.I, self.J
+        ld = (J + 31) // 32 * 32
+        med = C.c_double()
+        P = lambda tns: C.c_void_p(tns.data_ptr())  # noqa: E731
+        L.check(lib.wotb_cost_median_dev(h, P(self.x0), I, P(self.x1), J, D, None, C.byref(med)))
+        L.check(lib.wotb_cost_matrix_dev(h, P(self.x0), I, P(self.x1), J, D, None, med.value, P(self.C), ld, L.F32))
+        self.G[:I].copy_(self.G0)
+        infos = []
+        for it in range(GROWTH_ITERS):
+            if it > 0:
+                self.G[:I].copy_(self.rows[:I])
+            info = L.Info()
+            L.check(lib.wotb_sinkhorn_stored_dev(h, P(self.C), ld, I, J, P(self.G), C.byref(prm), P(self.f),
+                                                 P(self.g), P(self.rows), C.byref(info)))
+            infos.append(info.as_dict())
+        last = infos[-1]
+        L.check(lib.wotb_coupling_dev(h, P(self.C), ld, I, J, P(self.f), P(self.g), last["eps_final"],
+                                      last["out_scale"], P(self.out), J, L.F64, None))
+        return infos
+
+
+def matvec_bytes(info, I, J):
+    ld = (J + 31) // 32 * 32
+    n = 2 * info["iters"] + info["batches"][5] + 1     # half-steps + gap row sums + final row sums
+    return n * I * ld * 4, n
+
+
+def isolated_matvec(ctx, torch, I, J, reps=20):
+    """Average duration of one k_row and one k_col launch on an I x J kernel matrix (CUDA events on the
+    library's stream inside wotb_bench_matvec_dev)."""
+    ms_row, ms_col = C.c_double(), C.c_double()
+    from wot_b200 import _lib
+    _lib.check(ctx.lib.wotb_bench_matvec_dev(ctx.handle, I, J, reps, C.byref(ms_row), C.byref(ms_col)))
+    return ms_row.value, ms_col.value
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from wot_b200 import _lib, _pinned, synthetic
+    from wot_b200.ot import optimal_transport as wot_ot
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    ctx = _lib.Context(local_rank, stream.cuda_stream)
+    _lib._contexts[local_rank] = ctx
+    prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_STORED, **DEFAULTS)
+
+    pairs = synthetic.atlas_pairs(seed=1, scale=args.scale)
+    n_pairs = len(pairs)
+    max_i = max(p[0] for p in pairs)
+    max_j = max(p[1] for p in pairs)
+    total = args.warmup + args.steps
+    mine = [pairs[(s * world + rank) % n_pairs] for s in range(total)]
+    coords = {}
+    for p in set(mine):
+        coords[p] = synthetic.day_pair_coords(p[0], p[1], d=D, seed=p[2])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- leg 1: inputs resident in HBM, CUDA events on the library's stream ---------------------
+    dp = DevicePair(ctx, torch, max_i, max_j)
+    for s in range(args.warmup):
+        dp.load(*coords[mine[s]])
+        dp.run(prm)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    gpu_ms = 0.0
+    iters = launches = 0
+    mv_bytes = mv_launch = 0
+    solve_ms = 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s in range(args.warmup, total):
+        dp.load(*coords[mine[s]])           # synthetic coordinates placed in HBM outside the timed region
+        ev0.record(stream)
+        infos = dp.run(prm)
+        ev1.record(stream)
+        ev1.synchronize()
+        gpu_ms += ev0.elapsed_time(ev1)
+        for inf in infos:
+            iters += inf["iters"]
+            launches += inf["launches"]
+            solve_ms += inf["gpu_ms"]
+            b, n = matvec_bytes(inf, dp.I, dp.J)
+            mv_bytes += b
+            mv_launch += n
+        launches += 6 * 2 + 1 + 2 + 1       # median passes, cost (+pad), coupling
+    barrier()
+    clocks = sampler.stop()
+    t_dev = max_over_ranks(gpu_ms / 1e3)
+    total_steps = args.steps * world
+    value = total_steps / t_dev
+    iters_all = sum_over_ranks(iters)
+
+    # ---- leg 2: end to end through the host-buffer C ABI ---------------------------------------
+    del dp
+    torch.cuda.empty_cache()
+    pin_in = {}
+    for p in set(mine[args.warmup:] + mine[:1]):
+        x0, x1, g = coords[p]
+        bufs = []
+        for arr in (x0, x1, g):
+            pa = _pinned.empty(arr.shape, np.float64)
+            pa[...] = arr
+            bufs.append(pa)
+        pin_in[p] = bufs
+    out = _pinned.empty((max_i * max_j,), np.float64)
+
+    def e2e_step(p):
+        x0, x1, g = pin_in[p]
+        view = out[: p[0] * p[1]].reshape(p[0], p[1])
+        wot_ot.solve_coords(x0, x1, g, _lib.SOLVER_DUALITY_GAP, growth_iters=GROWTH_ITERS, kernel="stored",
+                            out=view, device=local_rank, **DEFAULTS)
+
+    e2e_step(mine[0])                        # warm the pinned bounce paths and workspaces
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for s in range(args.warmup, total):
+        p = mine[s]
+        e2e_step(p)
+        h2d += (p[0] + p[1]) * D * 8 + p[0] * 8
+        d2h += p[0] * p[1] * 8 + (GROWTH_ITERS + 1) * p[0] * 8 + (p[0] + p[1]) * 8
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_steps / t_e2e
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernels, measured live ----------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ri, rj = int(np.mean([p[0] for p in pairs])), int(np.mean([p[1] for p in pairs]))
+    ms_row, ms_col = isolated_matvec(ctx, torch, ri, rj)
+    ld = (rj + 31) // 32 * 32
+    alg = ri * ld * 4
+    achieved = 2 * alg / ((ms_row + ms_col) * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src,
+        "kernel": "k_row + k_col (stored-K matvec pair = one Sinkhorn iteration)",
+        "shape": [ri, rj], "algorithmic_bytes_per_launch": alg,
+        "row_ms": ms_row, "col_ms": ms_col,
+        "row_gbs": alg / (ms_row * 1e-3) / 1e9, "col_gbs": alg / (ms_col * 1e-3) / 1e9,
+        "in_solve_gbs": mv_bytes / (solve_ms * 1e-3) / 1e9,
+        "in_solve_note": "all matvec bytes of the timed steps / total solver device time incl. K builds and checks",
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        sec, m0, m1, it = cpu_reference_sample(pairs[0], args.cpu_cells, growth_iters=1)
+        mean_ij = float(np.mean([a * b for a, b, _ in pairs]))
+        sec_per_tmap = sec / (m0 * m1) * mean_ij * GROWTH_ITERS
+        cpu = {"value": 1.0 / sec_per_tmap, "unit": "tmaps/s", "cores": blas_threads(), "kind": "port",
+               "sample": "one full reference-port solve (%d iterations, dense primal/dual) of atlas pair 0 subsampled "
+                         "to %dx%d in %.1f s; seconds per entry scaled to the mean atlas pair and growth_iters=3"
+                         % (it, m0, m1, sec),
+               "iters_per_s_at_sample": it / sec}
+
+    line = {
+        "metric": "day-pair transport maps per second", "value": value, "unit": "tmaps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 K / f64 potentials",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "solver": "duality_gap", "kernel": "stored", "eps": 0.05, "lambda1": 1,
+                   "lambda2": 50, "l2": "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)",
+                   "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale},
+        "sinkhorn_iters_per_s": iters_all / t_dev,
+        "sinkhorn_iters": int(iters_all),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "tmaps/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import __graft_entry__
+    if rank == 0 and not os.path.exists(os.path.join(ROOT, "wot_b200", "csrc", "libwot_b200.so")):
+        __graft_entry__.build()
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+/*
+ * wot_b200.h -- C ABI of the B200-native Waddington-OT transport-map hot path.
+ *
+ * The reference (broadinstitute/wot) is pure Python and has no FFI; its seams for this path are
+ * Python call sites.  Every entry point below names the reference interface it replaces
+ * (file:line relative to the reference checkout); INTEGRATION.md shows the ctypes binding a wot
+ * maintainer would add at those call sites.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types cross this boundary.
+ *   - "_dev" entry points take DEVICE pointers on the context's device and enqueue on the
+ *     context's stream; they return after the work has completed unless stated otherwise.
+ *   - "_host" entry points take HOST pointers, copy in, compute on the GPU, copy out.
+ *   - matrices are row-major; "ld" arguments are leading dimensions in ELEMENTS.
+ *   - every function returns WOTB_OK (0) or a WOTB_ERR_* code; wotb_last_error() gives the text.
+ *   - a context is not thread-safe (the reference path is single-threaded, ot_model.py:182-199).
+ *   - there is NO CPU fallback: without a CUDA device wotb_create fails.
+ */
+#ifndef WOT_B200_H
+#define WOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WOTB_N_STAGES 6 /* epsilon_scalings + 1, optimal_transport.py:101,116 */
+
+enum wotb_error {
+    WOTB_OK = 0,
+    WOTB_ERR_INVALID = 1,  /* bad argument */
+    WOTB_ERR_CUDA = 2,     /* CUDA runtime error */
+    WOTB_ERR_NOMEM = 3,    /* device or pinned allocation failed */
+    WOTB_ERR_NAN_GAP = 4   /* optimal_transport.py:162-163: NaN duality gap -> RuntimeError */
+};
+
+enum wotb_solver {
+    WOTB_SOLVER_DUALITY_GAP = 0, /* optimal_transport_duality_gap, optimal_transport.py:67-164 */
+    WOTB_SOLVER_FIXED_ITERS = 1  /* transport_stablev2,            optimal_transport.py:167-236 */
+};
+
+enum wotb_kernel {
+    WOTB_KERNEL_STORED = 0, /* K = exp((u-C+v)/eps) kept in HBM as fp32; matvecs are HBM-bound   */
+    WOTB_KERNEL_ONLINE = 1  /* K recomputed tile by tile from coordinates; FP32/MUFU-bound        */
+};
+
+enum wotb_status {
+    WOTB_STATUS_CONVERGED = 0, /* returned R / J                          (optimal_transport.py:164) */
+    WOTB_STATUS_MAX_ITER = 1,  /* returned a*K*b, NOT divided by J        (optimal_transport.py:143-145) */
+    WOTB_STATUS_NAN = 2        /* final gap is NaN                        (optimal_transport.py:162-163) */
+};
+
+enum wotb_dtype { WOTB_F32 = 0, WOTB_F64 = 1 };
+
+/* The keys of OTModel.ot_config that reach the solvers (ot_model.py:85-87, splatted at :318). */
+typedef struct wotb_params {
+    double epsilon;
+    double lambda1;
+    double lambda2;
+    double epsilon0;
+    double tau;       /* stabilisation threshold; NaN means Python None (fixed_iters: no warm start) */
+    double tolerance;
+    double max_iter;  /* the reference passes 1e7 as a float */
+    int32_t batch_size;
+    int32_t scaling_iter;
+    int32_t extra_iter;
+    int32_t inner_iter_max;
+    int32_t solver; /* enum wotb_solver */
+    int32_t kernel; /* enum wotb_kernel */
+    int32_t use_graph; /* 1: replay the per-batch launch sequence as a CUDA graph */
+    int32_t reserved;
+} wotb_params;
+
+/* What the reference keeps as locals of the solver; returned for the parity criteria. */
+typedef struct wotb_info {
+    int64_t iters;                   /* current_iter                                   */
+    int32_t batches[WOTB_N_STAGES];  /* convergence checks per epsilon stage           */
+    int32_t tau_absorptions;         /* times optimal_transport.py:137-141 fired       */
+    int32_t status;                  /* enum wotb_status                               */
+    double gap;                      /* last duality_gap value                         */
+    double primal;
+    double dual;
+    double eps_final;                /* epsilon_i at return                            */
+    double out_scale;                /* 1/J, or 1 on the max_iter exit                 */
+    double gpu_ms;                   /* device time of the solve (CUDA events)         */
+    int64_t launches;                /* kernels launched by this call                  */
+    int64_t matvec_launches;         /* of which K.w / K^T.z matvec kernels            */
+} wotb_info;
+
+typedef struct wotb_ctx wotb_ctx;
+
+const char *wotb_version(void);
+const char *wotb_last_error(void);
+
+/* One context per (process, device).  cuda_stream may be NULL (context-owned stream) or a
+ * cudaStream_t created by the caller (e.g. torch.cuda.current_stream().cuda_stream). */
+int wotb_create(int device, void *cuda_stream, wotb_ctx **out);
+void wotb_destroy(wotb_ctx *ctx);
+int wotb_sync(wotb_ctx *ctx);
+/* Bytes of device memory currently held by the context's workspaces. */
+size_t wotb_workspace_bytes(const wotb_ctx *ctx);
+void wotb_release_workspace(wotb_ctx *ctx);
+
+/* ---- cost: replaces OTModel.compute_default_cost_matrix, ot_model.py:242-253 ------------------
+ * x0 [I,d], x1 [J,d] float64 row-major; scale [d] = singular values (the diagonal of `eigenvals`,
+ * ot_model.py:301) or NULL.  Distances are sum_k (x0_ik s_k - x1_jk s_k)^2 in float64 with the
+ * operation order of scipy cdist('sqeuclidean') (ot_model.py:249-251). */
+
+/* exact np.median over all I*J distances (ot_model.py:252): a 64-bit radix select that recomputes
+ * the distances each pass and never stores them.  *median_host receives the value. */
+int wotb_cost_median_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                         const double *scale, double *median_host);
+/* C[i*ldc + j] = dist_ij / median, rounded once to dtype (WOTB_F32 for the solver, WOTB_F64 for
+ * callers of compute_default_cost_matrix). median == 1.0 gives raw distances. */
+int wotb_cost_matrix_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                         const double *scale, double median, void *C, int64_t ldc, int32_t dtype);
+/* float64 [I,J] (ld_src) -> float32 [I,J] (ld_dst, padded columns zeroed); for caller-supplied costs. */
+int wotb_cost_to_f32_dev(wotb_ctx *ctx, const double *src, int64_t ld_src, int64_t I, int64_t J, float *dst,
+                         int64_t ld_dst);
+
+/* ---- solvers: replace the `solver(**params)` callable, optimal_transport.py:30 -----------------
+ * C [I, ldc] float32 device (ldc % 4 == 0, 16-byte aligned), G [I] float64 device.
+ * Outputs (device, float64): f [I] = u + eps log a, g [J] = v + eps log b, rowsum [I] = row sums
+ * of the returned coupling (what optimal_transport.py:27 and ot_model.py:319 take from tmap).
+ * The coupling itself is tmap_ij = exp((f_i + g_j - C_ij) / info->eps_final) * info->out_scale;
+ * materialise it with wotb_coupling_dev.  Both reference solvers are selected by params->solver. */
+int wotb_sinkhorn_stored_dev(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64_t J, const double *G,
+                             const wotb_params *params, double *f, double *g, double *rowsum, wotb_info *info);
+
+/* Online variant: never materialises C or K.  x0 [I,d], x1 [J,d] float64 device coordinates
+ * (already multiplied by `scale` if any), median from wotb_cost_median_dev. */
+int wotb_sinkhorn_online_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                             double median, const double *G, const wotb_params *params, double *f, double *g,
+                             double *rowsum, wotb_info *info);
+
+/* tmap[i*ldo + j] = exp((f_i + g_j - C_ij)/eps) * out_scale      (optimal_transport.py:153,164).
+ * rowsum may be NULL. out dtype WOTB_F32 or WOTB_F64. `out` may be device memory or pinned/mapped
+ * host memory reachable from the device. */
+int wotb_coupling_dev(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64_t J, const double *f,
+                      const double *g, double eps, double out_scale, void *out, int64_t ldo, int32_t dtype,
+                      double *rowsum);
+int wotb_coupling_online_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                             double median, const double *f, const double *g, double eps, double out_scale,
+                             void *out, int64_t ldo, int32_t dtype, double *rowsum);
+
+/* ---- host-buffer entry points: what a reference-side binding calls -----------------------------
+ * wotb_transport_map_from_cost_host replaces wot.ot.compute_transport_matrix(solver, C=..., G=...,
+ * growth_iters=..., **ot_config) (optimal_transport.py:10-33, called at ot_model.py:318).
+ *   C_host [I,J] float64, G_host [I] float64
+ *   tmap_host [I,J] (dtype out_dtype) or NULL; learned_growth_host [(growth_iters+1), I]: rows
+ *   0..growth_iters-1 are the G used by each growth iteration (optimal_transport.py:24-29), the last
+ *   row is tmap.sum(axis=1) (ot_model.py:319); f_host/g_host may be NULL; infos [growth_iters]. */
+int wotb_transport_map_from_cost_host(wotb_ctx *ctx, const double *C_host, int64_t I, int64_t J,
+                                      const double *G_host, const wotb_params *params, int32_t growth_iters,
+                                      void *tmap_host, int32_t out_dtype, double *learned_growth_host,
+                                      double *f_host, double *g_host, wotb_info *infos);
+
+/* wotb_transport_map_from_coords_host replaces ot_model.py:307-319: default cost (scaled
+ * coordinates, squared Euclidean, / median) followed by the growth loop.  scale_host may be NULL.
+ * median_out may be NULL.  params->kernel selects stored-K or online-K. */
+int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host,
+                                        int64_t J, int32_t d, const double *scale_host, const double *G_host,
+                                        const wotb_params *params, int32_t growth_iters, void *tmap_host,
+                                        int32_t out_dtype, double *learned_growth_host, double *f_host,
+                                        double *g_host, double *median_out, wotb_info *infos);
+
+/* replaces OTModel.compute_default_cost_matrix for callers that want the matrix itself (float64). */
+int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J,
+                                  int32_t d, const double *scale_host, double *C_host, double *median_out);
+
+/* Measurement hook for bench.py: average device time (ms, CUDA events on the context's stream) of one
+ * row-pass and one column-pass launch of the stored-K matvec kernels on an I x J kernel matrix. */
+int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col);
+
+/* Page-locked host memory for coupling outputs (cudaHostAlloc): a coupling written into it leaves the
+ * device at PCIe speed; pageable destinations are served through an internal bounce buffer. */
+int wotb_pinned_alloc(size_t bytes, void **out);
+void wotb_pinned_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WOT_B200_H */

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against golden vectors of the unmodified reference
+and against the float64 oracle.  Run on the B200 box with `-m gpu`.
+
+Tolerance (BASELINE.json north_star): max relative error <= 1e-4 on coupling entries (entries >= 1e-12 * max),
+row/column marginals, growth columns and dual potentials; final-stage batch count within +-1.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from tests.helpers import DEFAULTS, RTOL, assert_coupling_close, max_rel_err, pair_cost
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ot():
+    from wot_b200 import ot as _ot
+    return _ot
+
+
+def _solve(ot, name, C, G, **over):
+    params = dict(DEFAULTS, **over)
+    tmap = getattr(ot, name)(C=C, G=G, **params)
+    return tmap, ot.last_solve_info()
+
+
+def _check_potentials(info, f, g, eps):
+    # potentials enter the coupling as exp(f/eps): 1e-4 relative on entries <=> 1e-4 * eps absolute on f, g
+    assert np.max(np.abs(info["f"] - f)) <= RTOL * eps, np.max(np.abs(info["f"] - f))
+    assert np.max(np.abs(info["g"] - g)) <= RTOL * eps, np.max(np.abs(info["g"] - g))
+
+
+def test_reference_golden_case_identity(ot, golden):
+    """/root/reference/tests/test_transport.py:20-32."""
+    g = golden("ref_3x3")
+    for name, tag in (("optimal_transport_duality_gap", "dg"), ("transport_stablev2", "fx")):
+        tmap, _ = _solve(ot, name, g["C"], np.ones(3), epsilon=0.01)
+        assert np.allclose(tmap, np.eye(3), atol=0.01, rtol=0)
+        assert max_rel_err(tmap, g[tag + "_tmap"]) <= RTOL
+
+
+def test_reference_golden_case_through_otmodel(ot, golden):
+    """/root/reference/tests/test_transport.py:11-34 with the same API calls."""
+    from wot_b200._anndata import AnnData
+    rng = np.random.default_rng(18)
+    adata = AnnData(rng.random((6, 1000)), pd.DataFrame({"day": [1, 1, 1, 2, 2, 2]}),
+                    pd.DataFrame(index=np.arange(1000)))
+    cost = np.array([[0, 100, 100], [100, 0, 100], [100, 100, 0]])
+    model = ot.OTModel(adata, epsilon=0.01, lambda1=1, lambda2=50)
+    tmap = model.compute_transport_map(1, 2, cost_matrix=cost)
+    assert np.allclose(tmap.X, np.eye(3), atol=0.01, rtol=0)
+    g = golden("otmodel_3x3")
+    assert max_rel_err(tmap.X, g["tmap"]) <= RTOL
+    np.testing.assert_allclose(tmap.obs["g1"].values, g["g1"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("tag", ["small", "mid"])
+def test_default_solver_vs_reference(ot, golden, tag):
+    g = golden("dg_" + tag)
+    n0, n1, seed = (int(v) for v in g["shape"])
+    C, G = pair_cost(n0, n1, seed)
+    tmap, info = _solve(ot, "optimal_transport_duality_gap", C, G)
+    assert_coupling_close(tmap, g["dg_tmap"])
+    _check_potentials(info, g["dg_f"], g["dg_g"], 0.05)
+    got = info["infos"][0]
+    assert got["batches"][:5] == list(g["dg_batches"][:5])
+    assert abs(got["batches"][5] - int(g["dg_batches"][5])) <= 1
+    assert abs(got["iters"] - int(g["dg_iters"])) <= 5
+
+
+VARIATIONS = {
+    "eps01": dict(epsilon=0.01), "lam10_100": dict(lambda1=10, lambda2=100),
+    "loose": dict(epsilon=0.1, lambda1=0.1, lambda2=1), "batch7": dict(batch_size=7),
+    "tau1_2": dict(tau=1.2), "tau2_eps02": dict(tau=2.0, epsilon=0.02), "maxiter37": dict(max_iter=37),
+    "eps0_2": dict(epsilon0=2.0), "tol1e-5": dict(tolerance=1e-5),
+}
+
+
+@pytest.mark.parametrize("tag", sorted(VARIATIONS))
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_parameter_variations_vs_reference(ot, golden, tag, use_graph):
+    g = golden("dg_variations")
+    n0, n1, seed = (int(v) for v in g["shape"])
+    C, G = pair_cost(n0, n1, seed)
+    kw = VARIATIONS[tag]
+    tmap, info = _solve(ot, "optimal_transport_duality_gap", C, G, use_graph=use_graph, **kw)
+    assert_coupling_close(tmap, g[tag + "_tmap"])
+    eps_final = float(g[tag + "_eps_final"])
+    _check_potentials(info, g[tag + "_f"], g[tag + "_g"], eps_final)
+    got = info["infos"][0]
+    want_batches = [int(b) for b in g[tag + "_batches"]]
+    assert got["batches"][:5] == want_batches[:5], (got["batches"], want_batches)
+    assert abs(got["batches"][5] - want_batches[5]) <= 1
+    assert abs(got["eps_final"] - eps_final) <= 1e-15
+    if tag == "maxiter37":
+        assert got["iters"] == 37 and got["status"] == 1
+    if tag.startswith("tau"):
+        assert got["tau_absorptions"] > 0
+
+
+def test_fixed_iters_vs_reference(ot, golden):
+    g = golden("fixed_iters")
+    n0, n1, seed = (int(v) for v in g["shape"])
+    C, G = pair_cost(n0, n1, seed)
+    for tag, kw in (("default", {}), ("short", dict(scaling_iter=330, extra_iter=40, inner_iter_max=50)),
+                    ("tau1_5", dict(scaling_iter=400, extra_iter=50, tau=1.5))):
+        tmap, info = _solve(ot, "transport_stablev2", C, G, **kw)
+        assert_coupling_close(tmap, g[tag + "_tmap"])
+        _check_potentials(info, g[tag + "_f"], g[tag + "_g"], float(g[tag + "_eps_final"]))
+        want_iters = kw.get("scaling_iter", 3000) + kw.get("extra_iter", 1000)
+        assert info["infos"][0]["iters"] == want_iters
+
+
+def test_growth_loop_vs_reference(ot, golden):
+    g = golden("growth3")
+    n0, n1, seed = (int(v) for v in g["shape"])
+    C, G = pair_cost(n0, n1, seed)
+    tmap, learned = ot.compute_transport_matrix(ot.optimal_transport_duality_gap,
+                                                **dict(DEFAULTS, growth_iters=3, C=C, G=G.copy()))
+    assert_coupling_close(tmap, g["tmap"])
+    assert len(learned) == 3
+    np.testing.assert_allclose(np.array(learned), g["learned"], rtol=RTOL)
+
+
+def test_default_cost_vs_reference(ot, golden):
+    from wot_b200 import synthetic
+    g = golden("cost_default")
+    n0, n1, seed = (int(v) for v in g["shape"])
+    x0, x1, _ = synthetic.day_pair_coords(n0, n1, d=30, seed=seed)
+    got = ot.OTModel.compute_default_cost_matrix(x0, x1, np.diag(g["sv"]))
+    np.testing.assert_allclose(got, g["C"], rtol=1e-13, atol=0)
+    got7 = ot.OTModel.compute_default_cost_matrix(x0[:, :7], x1[:, :7])
+    np.testing.assert_allclose(got7, g["C_plain7"], rtol=1e-13, atol=0)
+
+
+def test_median_is_exact(ot):
+    """Radix select == np.median bit for bit, odd and even counts, ties, wide dimension."""
+    from scipy.spatial.distance import cdist
+    from wot_b200.ot import optimal_transport as impl
+    rng = np.random.default_rng(3)
+    for n0, n1, d in ((33, 35, 5), (64, 64, 30), (130, 77, 70), (257, 300, 30), (1, 1, 3), (2, 1, 4)):
+        x0, x1 = rng.normal(size=(n0, d)), rng.normal(size=(n1, d))
+        if n0 == 64:
+            x1[:32] = x0[:32]          # many exact zeros and ties
+        raw = cdist(x0, x1, metric="sqeuclidean")
+        C = impl.default_cost_matrix(x0, x1)
+        med = np.median(raw)
+        np.testing.assert_allclose(C * med, raw, rtol=1e-13, atol=1e-300)
+        assert np.median(C) == pytest.approx(1.0, abs=1e-15)
+
+
+def test_otmodel_default_path_vs_reference(ot, golden):
+    """PCA -> cost -> solver -> growth columns (ot_model.py:255-326) against the unmodified reference."""
+    from wot_b200 import synthetic
+    from wot_b200._anndata import AnnData
+    g = golden("otmodel_path")
+    cells = [int(c) for c in g["cells"]]
+    X, day, growth = synthetic.expression_matrix(cells, n_genes=int(g["n_genes"]), seed=int(g["seed"]))
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    adata = AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])]))
+    model = ot.OTModel(adata, growth_iters=2)
+    tm = model.compute_transport_map(0, 1)
+    assert list(tm.obs.index) == list(g["obs_index"]) and list(tm.var.index) == list(g["var_index"])
+    assert list(tm.obs.columns) == ["g0", "g1", "g2"]
+    assert_coupling_close(np.asarray(tm.X), g["tmap"])
+    for col in ("g0", "g1", "g2"):
+        np.testing.assert_allclose(tm.obs[col].values, g[col], rtol=RTOL)
+
+
+@pytest.mark.parametrize("shape", [(1500, 1637), (2000, 2000), (997, 4099), (4100, 513)])
+def test_default_solver_vs_oracle_from_coords(ot, shape):
+    """Config 1 scale: GPU default cost + solver from coordinates against the float64 oracle."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    n0, n1 = shape
+    x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=30, seed=n0 + n1)
+    info = orc.SolveInfo()
+    want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
+                                             gap="marginal", **DEFAULTS)
+    tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
+                                          G=growth.copy(), **DEFAULTS)
+    assert_coupling_close(tmap, want)
+    got = ot.last_solve_info()
+    _check_potentials(got, info.f, info.g, 0.05)
+    assert got["infos"][0]["batches"][:5] == info.batches[:5]
+    assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+    np.testing.assert_allclose(got["learned_growth"][-1], want.sum(axis=1), rtol=RTOL)
+
+
+def test_out_dtype_float32_and_out_buffer(ot):
+    C, G = pair_cost(200, 210, 5)
+    ref, _ = _solve(ot, "optimal_transport_duality_gap", C, G)
+    out = np.empty((200, 210), dtype=np.float32)
+    got, _ = _solve(ot, "optimal_transport_duality_gap", C, G, out=out, out_dtype=np.float32)
+    assert got is out
+    np.testing.assert_allclose(got, ref, rtol=2e-7, atol=1e-37)
+
+
+def test_fixed_point_property_large(ot):
+    """Size-independent property at an atlas-scale pair: the returned potentials satisfy the unbalanced
+    Sinkhorn fixed-point equations (optimal_transport.py:133-134) evaluated in float64 on the host."""
+    from wot_b200 import synthetic
+    n0, n1 = 6000, 7000
+    x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=30, seed=99)
+    tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
+                                          G=growth.copy(), **DEFAULTS)
+    info = ot.last_solve_info()
+    eps, l1, l2 = 0.05, 1.0, 50.0
+    f, g = info["f"], info["g"]
+    rows = tmap.sum(axis=1) * n1        # r_i = a_i (K b)_i
+    cols = tmap.sum(axis=0) * n1
+    # at a fixed point: a = (p / (K b dy))^alpha1 e^{-u/(l1+eps)}  <=>  r_i / J = p_i exp(-f_i / l1)
+    np.testing.assert_allclose(rows / n1, growth * np.exp(-f / l1), rtol=5e-4)
+    np.testing.assert_allclose(cols / n0, growth.mean() * np.exp(-g / l2), rtol=5e-4)
+    np.testing.assert_allclose(info["learned_growth"][-1], tmap.sum(axis=1), rtol=1e-6)

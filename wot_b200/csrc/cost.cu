@@ -1,0 +1,354 @@
+// Default cost of Waddington-OT on sm_100a: squared Euclidean distances between (singular-value
+// scaled) local-PCA coordinates, divided by the median of all I*J distances.
+//
+// Replaces OTModel.compute_default_cost_matrix, /root/reference/wot/ot/ot_model.py:242-253:
+//   :245-247  a.dot(eigenvals), b.dot(eigenvals)       -> k_scale_coords
+//   :249-251  pairwise_distances(metric='sqeuclidean') -> dist_tiles<> (float64, direct differences
+//             accumulated in dimension order like scipy's cdist, not the |x|^2+|y|^2-2xy expansion)
+//   :252      cost_matrix / np.median(cost_matrix)     -> exact 64-bit radix select that recomputes
+//             the distances each pass (6 digit passes), so the I x J float64 matrix the reference
+//             sorts through is never stored; then one pass writes dist/median rounded to fp32.
+// Also here: the coupling materialisation exp((f_i + g_j - C_ij)/eps)/J (optimal_transport.py:153,164).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace wotb {
+
+constexpr int kTile = 64;      // distances per CTA tile edge
+constexpr int kTileThreads = 256;
+constexpr int kChunk = 32;     // coordinate dimensions staged per shared-memory chunk
+constexpr int kTilePad = kTile + 2;
+
+__global__ void k_scale_coords(const double *__restrict__ x, const double *__restrict__ scale, double *__restrict__ out,
+                               long long n, int d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * d) out[idx] = scale ? __dmul_rn(x[idx], scale[idx % d]) : x[idx];
+}
+
+// Walks 64x64 tiles of the distance matrix; each thread owns a 4x4 micro-tile and hands every
+// finished distance to `sink(i, j, dist)`.  Accumulation order over dimensions is ascending with
+// separate subtract / multiply / add roundings (scipy cdist arithmetic), so every pass of the
+// median select and the final cost pass see bit-identical values.
+template <typename Sink>
+__device__ __forceinline__ void dist_tiles(const double *__restrict__ x0, long long I, const double *__restrict__ x1,
+                                           long long J, int d, Sink &sink) {
+    __shared__ double xs[kChunk][kTilePad];
+    __shared__ double ys[kChunk][kTilePad];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long tiles_i = (I + kTile - 1) / kTile, tiles_j = (J + kTile - 1) / kTile;
+    for (long long t = blockIdx.x; t < tiles_i * tiles_j; t += gridDim.x) {
+        const long long i0 = (t / tiles_j) * kTile, j0 = (t % tiles_j) * kTile;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        for (int k0 = 0; k0 < d; k0 += kChunk) {
+            const int kc = min(kChunk, d - k0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < kTile * kChunk; e += kTileThreads) {
+                const int k = e % kChunk, r = e / kChunk;
+                const long long gi = i0 + r, gj = j0 + r;
+                xs[k][r] = (k < kc && gi < I) ? x0[gi * d + k0 + k] : 0.0;
+                ys[k][r] = (k < kc && gj < J) ? x1[gj * d + k0 + k] : 0.0;
+            }
+            __syncthreads();
+            for (int k = 0; k < kc; ++k) {
+                double xv[4], yv[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) xv[r] = xs[k][ty * 4 + r];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yv[c] = ys[k][tx * 4 + c];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double df = __dsub_rn(xv[r], yv[c]);
+                        acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(df, df));
+                    }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sink.row(i0 + ty * 4 + r, j0 + tx * 4, acc[r], I, J);
+    }
+}
+
+// ---- cost matrix writer --------------------------------------------------------------------------
+template <typename T>
+struct CostSink {
+    T *C;
+    long long ldc;
+    double median;
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+        if (i >= I) return;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (j + c < J) C[i * ldc + j + c] = (T)__ddiv_rn(v[c], median);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kTileThreads) k_cost(const double *x0, long long I, const double *x1, long long J,
+                                                       int d, T *C, long long ldc, double median) {
+    CostSink<T> sink{C, ldc, median};
+    dist_tiles(x0, I, x1, J, d, sink);
+}
+
+// zero the padding columns [J, ldc) so vectorised readers may touch them
+__global__ void k_zero_pad(float *C, long long ldc, long long I, long long J) {
+    const long long pad = ldc - J;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pad > 0 && idx < I * pad) C[(idx / pad) * ldc + J + idx % pad] = 0.f;
+}
+
+__global__ void k_cost_to_f32(const double *__restrict__ src, long long ld_src, long long I, long long J,
+                              float *__restrict__ dst, long long ld_dst) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= I * ld_dst) return;
+    const long long i = idx / ld_dst, j = idx % ld_dst;
+    dst[idx] = j < J ? (float)src[i * ld_src + j] : 0.f;
+}
+
+// ---- exact median: MSB radix select over the float64 bit patterns --------------------------------
+// Non-negative doubles order like their bit patterns.  Digits, most significant first: 9 bits, then
+// five of 11 bits.  Each pass histograms the current digit of the values whose higher bits match
+// the prefix found so far; k_select_pick then walks the 2048 bins to the one holding the rank.
+constexpr int kSelBins = 2048;
+
+struct SelectState {
+    unsigned long long hist[kSelBins];
+    unsigned long long prefix;     // higher bits of the answer found so far
+    unsigned long long rank;       // rank still to find inside the prefix bucket
+    unsigned long long n_less;     // elements strictly below the prefix bucket
+    unsigned long long n_bucket;   // elements inside the prefix bucket
+    unsigned long long min_above;  // bit pattern of the smallest value above the selected one
+    int pass;
+};
+
+__host__ __device__ inline int sel_shift(int pass) { return pass == 0 ? 55 : 55 - 11 * pass; }
+__host__ __device__ inline int sel_bits(int pass) { return pass == 0 ? 9 : 11; }
+
+struct SelectSink {
+    unsigned int *hist;  // shared, kSelBins
+    unsigned long long prefix;
+    int pass;
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+        const int shift = sel_shift(pass), bits = sel_bits(pass);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[c]);
+            const bool in = i < I && j + c < J && (pass == 0 || (key >> (shift + bits)) == prefix);
+            const unsigned int digit = in ? (unsigned int)((key >> shift) & ((1u << bits) - 1u)) : 0xffffffffu;
+            // warp-aggregated shared atomics: early passes put nearly every value in a few bins
+            const unsigned int peers = __match_any_sync(0xffffffffu, digit);
+            if (in && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned int)__popc(peers));
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kTileThreads) k_select_hist(const double *x0, long long I, const double *x1,
+                                                              long long J, int d, SelectState *st) {
+    __shared__ unsigned int hist[kSelBins];
+    for (int b = threadIdx.x; b < kSelBins; b += kTileThreads) hist[b] = 0;
+    __syncthreads();
+    SelectSink sink{hist, st->prefix, st->pass};
+    dist_tiles(x0, I, x1, J, d, sink);
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSelBins; b += kTileThreads)
+        if (hist[b]) atomicAdd(&st->hist[b], (unsigned long long)hist[b]);
+}
+
+__global__ void k_select_pick(SelectState *st) {
+    if (threadIdx.x != 0) return;
+    const int bits = sel_bits(st->pass);
+    unsigned long long below = 0, rank = st->rank;
+    int digit = 0;
+    for (int b = 0; b < (1 << bits); ++b) {
+        const unsigned long long n = st->hist[b];
+        if (rank < below + n) {
+            digit = b;
+            st->n_bucket = n;
+            break;
+        }
+        below += n;
+    }
+    st->prefix = (st->prefix << bits) | (unsigned long long)digit;
+    st->rank = rank - below;
+    st->n_less += below;
+    st->pass += 1;
+    for (int b = 0; b < kSelBins; ++b) st->hist[b] = 0;
+}
+
+struct MinAboveSink {
+    unsigned long long key1;
+    unsigned long long best;
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[c]);
+            if (i < I && j + c < J && key > key1 && key < best) best = key;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kTileThreads) k_select_min_above(const double *x0, long long I, const double *x1,
+                                                                   long long J, int d, SelectState *st) {
+    MinAboveSink sink{st->prefix, ~0ull};
+    dist_tiles(x0, I, x1, J, d, sink);
+    unsigned long long best = sink.best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&st->min_above, best);
+}
+
+static int tile_grid(const wotb_ctx *ctx, int64_t I, int64_t J) {
+    const int64_t tiles = cdiv(I, kTile) * cdiv(J, kTile);
+    const int64_t cap = (int64_t)ctx->sm_count * 4;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+// coordinates multiplied by `scale` (or copied) into the context's staging buffer
+int scaled_coords(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
+                  const double **xs0, const double **xs1) {
+    if (!scale) {
+        *xs0 = x0;
+        *xs1 = x1;
+        return WOTB_OK;
+    }
+    WOTB_TRY(ctx->onl.reserve((size_t)(I + J) * d * 8 + 512));
+    double *a = ctx->onl.as<double>();
+    double *b = a + round_up(I * d, 32);
+    k_scale_coords<<<(unsigned)cdiv(I * d, 256), 256, 0, ctx->stream>>>(x0, scale, a, I, d);
+    k_scale_coords<<<(unsigned)cdiv(J * d, 256), 256, 0, ctx->stream>>>(x1, scale, b, J, d);
+    WOTB_CUDA(cudaGetLastError());
+    *xs0 = a;
+    *xs1 = b;
+    return WOTB_OK;
+}
+
+int scale_into(wotb_ctx *ctx, const double *x, int64_t n, int d, const double *scale, double *out) {
+    k_scale_coords<<<(unsigned)cdiv(n * d, 256), 256, 0, ctx->stream>>>(x, scale, out, n, d);
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
+                double *median_host) {
+    WOTB_REQUIRE(ctx && x0 && x1 && median_host, "NULL argument");
+    WOTB_REQUIRE(I >= 1 && J >= 1 && d >= 1, "I, J, d must be >= 1");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    const double *a, *b;
+    WOTB_TRY(scaled_coords(ctx, x0, I, x1, J, d, scale, &a, &b));
+    WOTB_TRY(ctx->select.reserve(sizeof(SelectState)));
+    SelectState *st = ctx->select.as<SelectState>();
+    const unsigned long long n = (unsigned long long)I * (unsigned long long)J;
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.rank = (n - 1) / 2;  // lower middle element; np.median averages it with the upper one for even n
+    init.min_above = ~0ull;
+    WOTB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = tile_grid(ctx, I, J);
+    for (int pass = 0; pass < 6; ++pass) {
+        k_select_hist<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
+        k_select_pick<<<1, 32, 0, ctx->stream>>>(st);
+    }
+    SelectState fin;
+    WOTB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
+    WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double lo, hi;
+    memcpy(&lo, &fin.prefix, 8);
+    hi = lo;
+    if (n % 2 == 0 && fin.n_less + fin.n_bucket <= n / 2) {
+        // the upper middle element is the smallest value strictly above `lo`
+        k_select_min_above<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
+        WOTB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
+        WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(&hi, &fin.min_above, 8);
+    }
+    WOTB_CUDA(cudaGetLastError());
+    *median_host = (lo + hi) / 2.0;
+    return WOTB_OK;
+}
+
+int cost_matrix(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
+                double median, void *C, int64_t ldc, int dtype) {
+    WOTB_REQUIRE(ctx && x0 && x1 && C, "NULL argument");
+    WOTB_REQUIRE(I >= 1 && J >= 1 && d >= 1 && ldc >= J, "bad shape");
+    WOTB_REQUIRE(dtype == WOTB_F32 || dtype == WOTB_F64, "dtype must be WOTB_F32 or WOTB_F64");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    const double *a, *b;
+    WOTB_TRY(scaled_coords(ctx, x0, I, x1, J, d, scale, &a, &b));
+    const int grid = tile_grid(ctx, I, J);
+    if (dtype == WOTB_F32) {
+        k_cost<float><<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, (float *)C, ldc, median);
+        if (ldc > J) k_zero_pad<<<(unsigned)cdiv(I * (ldc - J), 256), 256, 0, ctx->stream>>>((float *)C, ldc, I, J);
+    } else {
+        k_cost<double><<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, (double *)C, ldc, median);
+    }
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+int cost_to_f32(wotb_ctx *ctx, const double *src, int64_t ld_src, int64_t I, int64_t J, float *dst, int64_t ld_dst) {
+    WOTB_REQUIRE(ctx && src && dst && ld_src >= J && ld_dst >= J, "bad argument");
+    k_cost_to_f32<<<(unsigned)cdiv(I * ld_dst, 256), 256, 0, ctx->stream>>>(src, ld_src, I, J, dst, ld_dst);
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+// ---- coupling materialisation ------------------------------------------------------------------
+// tmap_ij = exp((f_i + g_j - C_ij)/eps) * scale, float64 argument and exp.  One CTA per row at a
+// time so the row sum (optimal_transport.py:27, ot_model.py:319) is a fixed-order block reduction.
+constexpr int kCoupThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kCoupThreads) k_coupling(const float *__restrict__ C, long long ldc, long long I,
+                                                           long long J, const double *__restrict__ f,
+                                                           const double *__restrict__ g, double inv_eps, double scale,
+                                                           T *__restrict__ out, long long ldo,
+                                                           double *__restrict__ rowsum) {
+    __shared__ double red[kCoupThreads / 32];
+    for (long long i = blockIdx.x; i < I; i += gridDim.x) {
+        const double fi = f[i];
+        double sum = 0.0;
+        for (long long j = threadIdx.x; j < J; j += kCoupThreads) {
+            const double v = exp((fi + g[j] - (double)C[i * ldc + j]) * inv_eps) * scale;
+            out[i * ldo + j] = (T)v;
+            sum += v;
+        }
+        if (rowsum) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < kCoupThreads / 32; ++w) tot += red[w];
+                rowsum[i] = tot;
+            }
+        }
+    }
+}
+
+int coupling(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64_t J, const double *f, const double *g,
+             double eps, double out_scale, void *out, int64_t ldo, int dtype, double *rowsum, cudaStream_t stream) {
+    WOTB_REQUIRE(ctx && C && f && g && out, "NULL argument");
+    WOTB_REQUIRE(ldc >= J && ldo >= J && eps > 0, "bad shape");
+    WOTB_REQUIRE(dtype == WOTB_F32 || dtype == WOTB_F64, "dtype must be WOTB_F32 or WOTB_F64");
+    const int grid = (int)(I < ctx->sm_count * 8 ? I : ctx->sm_count * 8);
+    if (dtype == WOTB_F32)
+        k_coupling<float><<<grid, kCoupThreads, 0, stream>>>(C, ldc, I, J, f, g, 1.0 / eps, out_scale, (float *)out, ldo,
+                                                              rowsum);
+    else
+        k_coupling<double><<<grid, kCoupThreads, 0, stream>>>(C, ldc, I, J, f, g, 1.0 / eps, out_scale, (double *)out,
+                                                               ldo, rowsum);
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+}  // namespace wotb

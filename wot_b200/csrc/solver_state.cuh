@@ -1,0 +1,65 @@
+// Device-resident state machine of one Sinkhorn solve.
+//
+// The reference drives its loop from Python (optimal_transport.py:116-164 / :204-232): every batch
+// it decides on the host whether to continue, absorb, change epsilon or stop.  Here that decision
+// lives on the GPU.  The host only replays one fixed launch sequence
+//     [build K if needed] (row matvec, column matvec) x B  [row sums for the gap]  [check]
+// and every kernel reads this block to decide whether it has work; the check kernel advances the
+// machine.  No host synchronisation sits between iterations, batches or epsilon stages.
+#pragma once
+
+#include "common.cuh"
+
+struct SolveCtrl {
+    // ---- constant for the solve ---------------------------------------------------------------
+    int I, J;
+    int solver;      // wotb_solver
+    int batch_size;  // final-stage iterations between duality-gap checks
+    int warm;        // fixed_iters: tau is not None
+    int scaling_iter, extra_iter, inner_iter_max;
+    double lambda1, lambda2, tau, tolerance, epsilon, epsilon0;
+    double eps_sched[WOTB_N_STAGES];  // epsilon_i of every stage, same recurrence as :113,:120
+    double max_iter;
+    double q;  // np.average(G), :108
+    // ---- advanced by the check kernel ---------------------------------------------------------
+    int stage;  // duality_gap: epsilon stage 0..5; fixed_iters: epsilon level
+    double eps, alpha1, alpha2, inv_l1e, inv_l2e;
+    int cur;          // which of a[2] / b[2] holds the current scalings
+    long long iter;   // current_iter
+    int batch_iters;  // iterations the current batch runs before the next check
+    int batch_done;   // iterations of the current batch already executed
+    int stop;         // bit0: tau exceeded (:137), bit1: max_iter reached (:143)
+    int tau_check;    // 0 in the extra_iter phase of fixed_iters (:230-232 has no stabilisation)
+    int need_build;   // K must be rebuilt from (u, v, C, eps) before the next iteration
+    int done;
+    int status;  // wotb_status
+    int batches[WOTB_N_STAGES];
+    int tau_count;
+    double gap, primal, dual, sumK0;
+    int phase;  // fixed_iters: 0 scaling loop, 1 extra loop
+    int since;  // iterations_since_epsilon_adjusted
+    int scaling_done;
+    // ---- scratch written by the matvec kernels ------------------------------------------------
+    unsigned long long maxabs;  // bit pattern of max(|a|, |b|) over the current iteration
+    unsigned int col_tiles_done;
+    unsigned int pad0;
+    unsigned long long seq;  // check kernels executed so far
+    double eps_final, out_scale;
+};
+
+// Pointers into the per-solve vector workspace (all device memory, fixed for the solve).
+struct SolveVecs {
+    const double *p;  // G, row masses
+    double *u, *v;    // absorbed dual potentials
+    double *a[2], *b[2];
+    double *eu, *ev;  // exp(-u/(lambda1+eps)), exp(-v/(lambda2+eps)): constant between absorptions
+    double *s, *t;    // K (b dy) and K^T (a dx) of the last matvecs
+    double *r, *c;    // row / column sums of R = a K b at the last gap check
+    double *f, *g;    // outputs
+    float *w, *z;     // fp32 copies of b*dy and a*dx fed to the matvecs (w padded to ld with zeros)
+    double *colpart;  // [n_row_blocks, ldp] column partial sums
+    unsigned int *tile_counters;
+    double *sumK0_part;
+    int n_sumK0_part;
+    long long ldp;
+};
