@@ -70,7 +70,7 @@ typedef struct wotb_params {
     int32_t solver; /* enum wotb_solver */
     int32_t kernel; /* enum wotb_kernel */
     int32_t use_graph; /* 1: replay the per-batch launch sequence as a CUDA graph */
-    int32_t reserved;
+    int32_t reserved;  /* flags; bit0 = 1 disables the fused one-sweep iteration kernel (two matvec kernels instead) */
 } wotb_params;
 
 /* What the reference keeps as locals of the solver; returned for the parity criteria. */
@@ -172,7 +172,8 @@ int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t 
 
 /* Measurement hook for bench.py: average device time (ms, CUDA events on the context's stream) of one
  * row-pass and one column-pass launch of the stored-K matvec kernels on an I x J kernel matrix. */
-int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col);
+int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
+                          double *ms_fused /* one fused iteration (K read once), -1 if the shape is unsupported */);
 
 /* Page-locked host memory for coupling outputs (cudaHostAlloc): a coupling written into it leaves the
  * device at PCIe speed; pageable destinations are served through an internal bounce buffer. */

@@ -78,13 +78,13 @@ VARIATIONS = {
 
 
 @pytest.mark.parametrize("tag", sorted(VARIATIONS))
-@pytest.mark.parametrize("use_graph", [True, False])
-def test_parameter_variations_vs_reference(ot, golden, tag, use_graph):
+@pytest.mark.parametrize("use_graph,fuse", [(True, True), (False, True), (True, False)])
+def test_parameter_variations_vs_reference(ot, golden, tag, use_graph, fuse):
     g = golden("dg_variations")
     n0, n1, seed = (int(v) for v in g["shape"])
     C, G = pair_cost(n0, n1, seed)
     kw = VARIATIONS[tag]
-    tmap, info = _solve(ot, "optimal_transport_duality_gap", C, G, use_graph=use_graph, **kw)
+    tmap, info = _solve(ot, "optimal_transport_duality_gap", C, G, use_graph=use_graph, fuse=fuse, **kw)
     assert_coupling_close(tmap, g[tag + "_tmap"])
     eps_final = float(g[tag + "_eps_final"])
     _check_potentials(info, g[tag + "_f"], g[tag + "_g"], eps_final)
@@ -168,8 +168,10 @@ def test_otmodel_default_path_vs_reference(ot, golden):
         np.testing.assert_allclose(tm.obs[col].values, g[col], rtol=RTOL)
 
 
-@pytest.mark.parametrize("shape", [(1500, 1637), (2000, 2000), (997, 4099), (4100, 513)])
-def test_default_solver_vs_oracle_from_coords(ot, shape):
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("shape", [(1500, 1637), (2000, 2000), (997, 4099), (4100, 513), (300, 19000), (130, 23040),
+                                   (200, 24001)])
+def test_default_solver_vs_oracle_from_coords(ot, shape, fuse):
     """Config 1 scale: GPU default cost + solver from coordinates against the float64 oracle."""
     from oracle import wot_oracle as orc
     from wot_b200 import synthetic
@@ -179,7 +181,7 @@ def test_default_solver_vs_oracle_from_coords(ot, shape):
     want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
                                              gap="marginal", **DEFAULTS)
     tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
-                                          G=growth.copy(), **DEFAULTS)
+                                          G=growth.copy(), fuse=fuse, **DEFAULTS)
     assert_coupling_close(tmap, want)
     got = ot.last_solve_info()
     _check_potentials(got, info.f, info.g, 0.05)

@@ -68,7 +68,7 @@ SIGNATURES = {
     "wotb_transport_map_from_coords_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, C.POINTER(Params), _I32,
                                                       _P, _I32, _P, _P, _P, C.POINTER(_D), C.POINTER(Info)]),
     "wotb_default_cost_matrix_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, C.POINTER(_D)]),
-    "wotb_bench_matvec_dev": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D)]),
+    "wotb_bench_matvec_dev": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "wotb_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "wotb_pinned_free": (None, [_P]),
 }
@@ -113,7 +113,7 @@ def check(rc):
 
 def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tolerance=1e-8, max_iter=1e7,
                 batch_size=5, scaling_iter=3000, extra_iter=1000, inner_iter_max=50, solver=SOLVER_DUALITY_GAP,
-                kernel=KERNEL_STORED, use_graph=True, **ignored):
+                kernel=KERNEL_STORED, use_graph=True, fuse=True, **ignored):
     """Pack the ot_config keys the solvers read (ot_model.py:85-87).  Unknown keys are ignored, like the
     reference solvers' **ignored."""
     p = Params()
@@ -123,6 +123,7 @@ def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tole
     p.batch_size, p.scaling_iter = int(batch_size), int(scaling_iter)
     p.extra_iter, p.inner_iter_max = int(extra_iter), int(inner_iter_max)
     p.solver, p.kernel, p.use_graph = int(solver), int(kernel), int(bool(use_graph))
+    p.reserved = 0 if fuse else 1   # bit0: disable the fused (K-read-once) iteration kernel
     return p
 
 

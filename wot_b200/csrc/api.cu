@@ -434,8 +434,9 @@ int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t 
                                    });
 }
 
-int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col) {
-    return bench_matvec(ctx, I, J, reps, ms_row, ms_col);
+int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
+                          double *ms_fused) {
+    return bench_matvec(ctx, I, J, reps, ms_row, ms_col, ms_fused);
 }
 
 int wotb_pinned_alloc(size_t bytes, void **out) {

@@ -297,6 +297,10 @@ __global__ void __launch_bounds__(kColThreads) k_col(const float *__restrict__ K
     }
 }
 
+}  // namespace wotb
+#include "fused_iter.cuh"
+namespace wotb {
+
 // ------------------------------------------------------------------------------------------------
 // State machine: one CTA, O(I + J) float64 work.
 // ------------------------------------------------------------------------------------------------
@@ -617,7 +621,10 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     const size_t o_k0 = take(off, (size_t)n_k0_part * 8 + 64);
     WOTB_TRY(ctx->vec.reserve(off));
     const int64_t ldp = round_up(ldw, 4);
-    WOTB_TRY(ctx->part.reserve((size_t)n_row_blocks * ldp * 8));
+    {
+        const size_t unfused = (size_t)n_row_blocks * ldp * 8, fused = (size_t)ctx->sm_count * ldw * 4;
+        WOTB_TRY(ctx->part.reserve(unfused > fused ? unfused : fused));
+    }
     char *base = ctx->vec.as<char>();
     SolveVecs V;
     V.p = G;
@@ -836,11 +843,27 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
     const dim3 col_grid(n_col_tiles, n_row_blocks);
     const int slots = h.solver == WOTB_SOLVER_DUALITY_GAP ? 5 : 10;
     volatile int *host_done = ctx->status.as<int>();
+    const FusePlan plan = (prm->reserved & 1) ? FusePlan() : plan_fused(ctx, I, ld);
+    float *part_f = ctx->part.as<float>();
+    const int finish_grid = (int)cdiv(J, kFinishThreads);
+    if (plan.ok) {  // sets the dynamic shared memory attribute outside of any stream capture
+        SolveCtrl idle = h;
+        idle.done = 1;
+        WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &idle, sizeof(idle), cudaMemcpyHostToDevice, st));
+        WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f));
+        WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+        launch_init(ctx, V, d_ctrl, ld);
+    }
     auto sequence = [&]() {
         k_build<<<build_grid, kBuildThreads, 0, st>>>(C, ldc, K, ld, V, d_ctrl);
         for (int s = 0; s < slots; ++s) {
-            k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 0, nullptr);
-            k_col<<<col_grid, kColThreads, 0, st>>>(K, ld, V, d_ctrl, rows_per_block);
+            if (plan.ok) {
+                launch_fused(plan, st, K, ld, V, d_ctrl, part_f);
+                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
+            } else {
+                k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 0, nullptr);
+                k_col<<<col_grid, kColThreads, 0, st>>>(K, ld, V, d_ctrl, rows_per_block);
+            }
         }
         if (h.solver == WOTB_SOLVER_DUALITY_GAP) k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 1, nullptr);
         launch_check(ctx, V, d_ctrl, host_done);
@@ -883,7 +906,7 @@ __global__ void k_fill(float *x, long long n, float v) {
 }
 
 // Average device time of the two matvec kernels on an I x J kernel matrix (bench.py roofline leg).
-int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, double *ms_col) {
+int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, double *ms_col, double *ms_fused) {
     WOTB_REQUIRE(ctx && ms_row && ms_col && I >= 1 && J >= 1 && reps >= 1, "bad argument");
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -933,6 +956,28 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
     WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     *ms_col = ms / reps;
     WOTB_CUDA(cudaGetLastError());
+    if (ms_fused) {
+        *ms_fused = -1.0;
+        const FusePlan plan = plan_fused(ctx, I, ld);
+        if (plan.ok) {
+            float *part_f = ctx->part.as<float>();
+            const int finish_grid = (int)cdiv(J, kFinishThreads);
+            for (int w = 0; w < 3; ++w) {
+                WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f));
+                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
+            }
+            WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
+            for (int r = 0; r < reps; ++r) {
+                launch_fused(plan, st, K, ld, V, d_ctrl, part_f);
+                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
+            }
+            WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
+            WOTB_CUDA(cudaStreamSynchronize(st));
+            WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            *ms_fused = ms / reps;
+            WOTB_CUDA(cudaGetLastError());
+        }
+    }
     return WOTB_OK;
 }
 
