@@ -61,6 +61,13 @@ __device__ __forceinline__ void atomic_max_nonneg(unsigned long long *addr, doub
     if (x == x) atomicMax(addr, (unsigned long long)__double_as_longlong(x));
 }
 
+// a = (p / s)^alpha * exp(-u/(lambda+eps))  (optimal_transport.py:133-134) evaluated as
+// exp(alpha (log p - log s) + lu): one log and one exp instead of a divide, a pow and a multiply, which
+// is what keeps the per-row scalar work of the fused kernel off the critical path.
+__device__ __forceinline__ double scaling_update(double log_mass, double s, double alpha, double log_damp) {
+    return exp(fma(alpha, log_mass - log(s), log_damp));
+}
+
 __device__ __forceinline__ bool iteration_active(const SolveCtrl *c) {
     return !c->done && c->stop == 0 && c->batch_done < c->batch_iters;
 }
@@ -80,6 +87,7 @@ constexpr int kBuildThreads = 256;
 __global__ void __launch_bounds__(kBuildThreads) k_build(const float *__restrict__ C, long long ldc,
                                                          float *__restrict__ K, long long ld, SolveVecs V,
                                                          SolveCtrl *ctrl) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->grid_bar = 0;  // head of every launch sequence
     if (ctrl->done || !ctrl->need_build) return;
     __shared__ double red[33];
     const int I = ctrl->I, J = ctrl->J;
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row(const float *__restrict__ K
         acc = warp_sum(acc);
         if (lane == 0) {
             if (mode == 0) {
-                const double a = pow(V.p[row] / acc, alpha1) * V.eu[row];
+                const double a = scaling_update(V.lp[row], acc, alpha1, V.lu[row]);
                 a_out[row] = a;
                 V.s[row] = acc;
                 V.z[row] = (float)(a * dx);
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kColThreads) k_col(const float *__restrict__ K
     if (!is_last) return;
     __threadfence();
     const double alpha2 = ctrl->alpha2;
-    const double qmass = ctrl->q;
+    const double lq = ctrl->lq;
     const double dy = 1.0 / (double)J;
     double *b_out = V.b[cur ^ 1];
     double bmax = 0.0;
@@ -275,7 +283,7 @@ __global__ void __launch_bounds__(kColThreads) k_col(const float *__restrict__ K
         if (j < J) {
             double t = 0.0;
             for (int rb = 0; rb < (int)gridDim.y; ++rb) t += __ldcg(V.colpart + (long long)rb * V.ldp + j);
-            const double b = pow(qmass / t, alpha2) * V.ev[j];
+            const double b = scaling_update(lq, t, alpha2, V.lv[j]);
             b_out[j] = b;
             V.t[j] = t;
             V.w[j] = (float)(b * dy);
@@ -326,14 +334,14 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
         const double u = V.u[i] + eps_abs * log(a[i]);
         V.u[i] = u;
         a[i] = 1.0;
-        V.eu[i] = exp(-u * i1);
+        V.lu[i] = -u * i1;
         V.z[i] = dxf;
     }
     for (int j = threadIdx.x; j < J; j += kCheckThreads) {
         const double v = V.v[j] + eps_abs * log(b[j]);
         V.v[j] = v;
         b[j] = 1.0;
-        V.ev[j] = exp(-v * i2);
+        V.lv[j] = -v * i2;
         V.w[j] = dyf;
     }
 }
@@ -576,7 +584,8 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
         V.u[i] = 0.0;
         V.a[0][i] = 1.0;
         V.a[1][i] = 1.0;
-        V.eu[i] = 1.0;
+        V.lu[i] = 0.0;
+        V.lp[i] = log(V.p[i]);
         V.z[i] = dxf;
         V.s[i] = 0.0;
     }
@@ -585,13 +594,16 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
             V.v[j] = 0.0;
             V.b[0][j] = 1.0;
             V.b[1][j] = 1.0;
-            V.ev[j] = 1.0;
+            V.lv[j] = 0.0;
             V.t[j] = 0.0;
         }
         V.w[j] = j < J ? dyf : 0.f;
     }
     sum = block_sum<kCheckThreads>(sum, red);
-    if (threadIdx.x == 0) ctrl->q = sum / (double)I;
+    if (threadIdx.x == 0) {
+        ctrl->q = sum / (double)I;
+        ctrl->lq = log(sum / (double)I);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -615,6 +627,7 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     const size_t o_u = take(off, dI), o_v = take(off, dJ);
     const size_t o_a0 = take(off, dI), o_a1 = take(off, dI), o_b0 = take(off, dJ), o_b1 = take(off, dJ);
     const size_t o_eu = take(off, dI), o_ev = take(off, dJ), o_s = take(off, dI), o_t = take(off, dJ);
+    const size_t o_lp = take(off, dI);
     const size_t o_r = take(off, dI), o_c = take(off, dJ);
     const size_t o_w = take(off, (size_t)ldw * 4), o_z = take(off, (size_t)I * 4);
     const size_t o_tc = take(off, (size_t)n_col_tiles * 4 + 64);
@@ -634,8 +647,9 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.a[1] = (double *)(base + o_a1);
     V.b[0] = (double *)(base + o_b0);
     V.b[1] = (double *)(base + o_b1);
-    V.eu = (double *)(base + o_eu);
-    V.ev = (double *)(base + o_ev);
+    V.lu = (double *)(base + o_eu);
+    V.lv = (double *)(base + o_ev);
+    V.lp = (double *)(base + o_lp);
     V.s = (double *)(base + o_s);
     V.t = (double *)(base + o_t);
     V.r = (double *)(base + o_r);
@@ -845,22 +859,20 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
     volatile int *host_done = ctx->status.as<int>();
     const FusePlan plan = (prm->reserved & 1) ? FusePlan() : plan_fused(ctx, I, ld);
     float *part_f = ctx->part.as<float>();
-    const int finish_grid = (int)cdiv(J, kFinishThreads);
     if (plan.ok) {  // sets the dynamic shared memory attribute outside of any stream capture
         SolveCtrl idle = h;
         idle.done = 1;
         WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &idle, sizeof(idle), cudaMemcpyHostToDevice, st));
-        WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f));
+        WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f, 1));
         WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
         launch_init(ctx, V, d_ctrl, ld);
     }
     auto sequence = [&]() {
         k_build<<<build_grid, kBuildThreads, 0, st>>>(C, ldc, K, ld, V, d_ctrl);
-        for (int s = 0; s < slots; ++s) {
-            if (plan.ok) {
-                launch_fused(plan, st, K, ld, V, d_ctrl, part_f);
-                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
-            } else {
+        if (plan.ok) {
+            launch_fused(plan, st, K, ld, V, d_ctrl, part_f, slots);  // one cooperative launch per batch
+        } else {
+            for (int s = 0; s < slots; ++s) {
                 k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 0, nullptr);
                 k_col<<<col_grid, kColThreads, 0, st>>>(K, ld, V, d_ctrl, rows_per_block);
             }
@@ -868,9 +880,9 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
         if (h.solver == WOTB_SOLVER_DUALITY_GAP) k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 1, nullptr);
         launch_check(ctx, V, d_ctrl, host_done);
     };
-    const int per_seq = 2 + 2 * slots + (h.solver == WOTB_SOLVER_DUALITY_GAP ? 1 : 0);
+    const int per_seq = 2 + (plan.ok ? 1 : 2 * slots) + (h.solver == WOTB_SOLVER_DUALITY_GAP ? 1 : 0);
     info->launches = 1;
-    int rc = pump(ctx, prm->use_graph != 0, per_seq, 2 * slots, sequence, info);
+    int rc = pump(ctx, prm->use_graph != 0, per_seq, plan.ok ? 1 : 2 * slots, sequence, info);
     if (rc != WOTB_OK) return rc;
 
     WOTB_CUDA(cudaMemcpyAsync(&h, d_ctrl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -961,19 +973,22 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
         const FusePlan plan = plan_fused(ctx, I, ld);
         if (plan.ok) {
             float *part_f = ctx->part.as<float>();
-            const int finish_grid = (int)cdiv(J, kFinishThreads);
-            for (int w = 0; w < 3; ++w) {
-                WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f));
-                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
-            }
+            const int per_launch = 5;
+            SolveCtrl zero_bar = h;
+            auto reset = [&]() { return cudaMemcpyAsync(d_ctrl, &zero_bar, sizeof(zero_bar), cudaMemcpyHostToDevice, st); };
+            WOTB_CUDA(reset());
+            WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f, per_launch));
+            const int launches = (reps + per_launch - 1) / per_launch;
+            WOTB_CUDA(reset());
             WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
-            for (int r = 0; r < reps; ++r) {
-                launch_fused(plan, st, K, ld, V, d_ctrl, part_f);
-                k_col_finish<<<finish_grid, kFinishThreads, 0, st>>>(part_f, ld, plan.grid, V, d_ctrl);
+            for (int r = 0; r < launches; ++r) {
+                launch_fused(plan, st, K, ld, V, d_ctrl, part_f, per_launch);
+                k_fill<<<1, 32, 0, st>>>((float *)&d_ctrl->grid_bar, 1, 0.f);  // what k_build does in a solve
             }
             WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
             WOTB_CUDA(cudaStreamSynchronize(st));
             WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            reps = launches * per_launch;
             *ms_fused = ms / reps;
             WOTB_CUDA(cudaGetLastError());
         }

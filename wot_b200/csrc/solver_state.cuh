@@ -20,7 +20,8 @@ struct SolveCtrl {
     double lambda1, lambda2, tau, tolerance, epsilon, epsilon0;
     double eps_sched[WOTB_N_STAGES];  // epsilon_i of every stage, same recurrence as :113,:120
     double max_iter;
-    double q;  // np.average(G), :108
+    double q;   // np.average(G), :108
+    double lq;  // log q
     // ---- advanced by the check kernel ---------------------------------------------------------
     int stage;  // duality_gap: epsilon stage 0..5; fixed_iters: epsilon level
     double eps, alpha1, alpha2, inv_l1e, inv_l2e;
@@ -42,7 +43,7 @@ struct SolveCtrl {
     // ---- scratch written by the matvec kernels ------------------------------------------------
     unsigned long long maxabs;  // bit pattern of max(|a|, |b|) over the current iteration
     unsigned int col_tiles_done;
-    unsigned int pad0;
+    unsigned int grid_bar;  // arrival counter of the fused kernel's grid barrier (zeroed by k_build)
     unsigned long long seq;  // check kernels executed so far
     double eps_final, out_scale;
 };
@@ -52,7 +53,8 @@ struct SolveVecs {
     const double *p;  // G, row masses
     double *u, *v;    // absorbed dual potentials
     double *a[2], *b[2];
-    double *eu, *ev;  // exp(-u/(lambda1+eps)), exp(-v/(lambda2+eps)): constant between absorptions
+    double *lu, *lv;  // -u/(lambda1+eps), -v/(lambda2+eps): log of the damping factors, constant between absorptions
+    double *lp;       // log p (row masses), constant for the solve
     double *s, *t;    // K (b dy) and K^T (a dx) of the last matvecs
     double *r, *c;    // row / column sums of R = a K b at the last gap check
     double *f, *g;    // outputs
