@@ -216,3 +216,46 @@ def test_fixed_point_property_large(ot):
     np.testing.assert_allclose(rows / n1, growth * np.exp(-f / l1), rtol=5e-4)
     np.testing.assert_allclose(cols / n0, growth.mean() * np.exp(-g / l2), rtol=5e-4)
     np.testing.assert_allclose(info["learned_growth"][-1], tmap.sum(axis=1), rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# online kernel (K recomputed from coordinates, never stored)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,d", [((1500, 1637), 30), ((2000, 2000), 30), ((700, 3001), 30), ((3001, 700), 30),
+                                     ((900, 1000), 5), ((600, 650), 50), ((130, 129), 33)])
+def test_online_kernel_vs_oracle(ot, shape, d):
+    """exp((f_i + g_j - C_ij)/eps) recomputed tile by tile: same couplings, potentials and batch counts."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    n0, n1 = shape
+    x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=d, seed=n0 + n1 + d)
+    info = orc.SolveInfo()
+    want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
+                                             gap="marginal", **DEFAULTS)
+    tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
+                                          G=growth.copy(), kernel="online", **DEFAULTS)
+    rep = assert_coupling_close(tmap, want)
+    got = ot.last_solve_info()
+    _check_potentials(got, info.f, info.g, 0.05)
+    assert got["infos"][0]["batches"][:5] == info.batches[:5], rep
+    assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+    np.testing.assert_allclose(got["learned_growth"][-1], want.sum(axis=1), rtol=RTOL)
+
+
+def test_online_kernel_growth_scale_and_fixed_iters(ot):
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    x0, x1, growth = synthetic.day_pair_coords(500, 560, d=30, seed=77)
+    sv = np.linspace(3.0, 0.5, 30)
+    cost = orc.compute_default_cost_matrix(x0, x1, np.diag(sv))
+    params = dict(DEFAULTS, growth_iters=2)
+    want, learned = orc.compute_transport_matrix(orc.optimal_transport_duality_gap, C=cost, G=growth.copy(), **params)
+    tmap, got_learned = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, sv), C=None,
+                                                    G=growth.copy(), kernel="online", **params)
+    assert_coupling_close(tmap, want)
+    np.testing.assert_allclose(np.array(got_learned), np.array(learned), rtol=RTOL)
+    short = dict(DEFAULTS, scaling_iter=330, extra_iter=40, inner_iter_max=50)
+    want = orc.transport_stablev2(C=cost, G=growth, **short)
+    tmap, _ = ot.compute_transport_matrix(ot.transport_stablev2, coords=(x0, x1, sv), C=None, G=growth.copy(),
+                                          kernel="online", **short)
+    assert_coupling_close(tmap, want)

@@ -351,4 +351,47 @@ int coupling(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64_t J, c
     return WOTB_OK;
 }
 
+// Coupling straight from coordinates (online kernel: C is never stored); float64 distances, argument
+// and exp, like the stored path.
+template <typename T>
+struct CouplingSink {
+    T *out;
+    long long ldo;
+    const double *f, *g;
+    double inv_median, inv_eps, scale;
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+        if (i >= I) return;
+        const double fi = f[i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (j + c < J) out[i * ldo + j + c] = (T)(exp((fi + g[j + c] - v[c] * inv_median) * inv_eps) * scale);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kTileThreads) k_coupling_online(const double *x0, long long I, const double *x1,
+                                                                  long long J, int d, CouplingSink<T> sink) {
+    dist_tiles(x0, I, x1, J, d, sink);
+}
+
+int coupling_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
+                    const double *f, const double *g, double eps, double out_scale, void *out, int64_t ldo, int dtype,
+                    double *rowsum, cudaStream_t stream) {
+    WOTB_REQUIRE(ctx && x0 && x1 && f && g && out, "NULL argument");
+    WOTB_REQUIRE(ldo >= J && eps > 0 && median > 0, "bad shape");
+    WOTB_REQUIRE(rowsum == nullptr, "row sums of the online coupling come from wotb_sinkhorn_online_dev");
+    const int grid = tile_grid(ctx, I, J);
+    if (dtype == WOTB_F32) {
+        CouplingSink<float> sink{(float *)out, ldo, f, g, 1.0 / median, 1.0 / eps, out_scale};
+        k_coupling_online<float><<<grid, kTileThreads, 0, stream>>>(x0, I, x1, J, d, sink);
+    } else if (dtype == WOTB_F64) {
+        CouplingSink<double> sink{(double *)out, ldo, f, g, 1.0 / median, 1.0 / eps, out_scale};
+        k_coupling_online<double><<<grid, kTileThreads, 0, stream>>>(x0, I, x1, J, d, sink);
+    } else {
+        WOTB_REQUIRE(false, "dtype must be WOTB_F32 or WOTB_F64");
+    }
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
 }  // namespace wotb

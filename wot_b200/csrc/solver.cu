@@ -320,6 +320,8 @@ __device__ void set_eps(SolveCtrl *c, double eps) {
     c->alpha2 = c->lambda2 / (c->lambda2 + eps);
     c->inv_l1e = 1.0 / (c->lambda1 + eps);
     c->inv_l2e = 1.0 / (c->lambda2 + eps);
+    c->c1 = 1.4426950408889634 / eps;
+    c->c2 = c->c1 * c->inv_median;
 }
 
 // u += eps log a, v += eps log b, a = b = 1 (:118-119, :138-141, :212-216, :221-228) and refresh
@@ -329,20 +331,34 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
     const int I = c->I, J = c->J;
     const double i1 = 1.0 / (c->lambda1 + eps_next), i2 = 1.0 / (c->lambda2 + eps_next);
     const float dxf = (float)(1.0 / (double)I), dyf = (float)(1.0 / (double)J);
+    const double c1 = 1.4426950408889634 / eps_next, c2 = c1 * c->inv_median;
+    const double l2dx = -log2((double)I), l2dy = -log2((double)J);
     double *a = V.a[cur], *b = V.b[cur];
     for (int i = threadIdx.x; i < I; i += kCheckThreads) {
         const double u = V.u[i] + eps_abs * log(a[i]);
         V.u[i] = u;
         a[i] = 1.0;
         V.lu[i] = -u * i1;
-        V.z[i] = dxf;
+        if (V.online) {
+            const double ps = c1 * u - c2 * V.nx[i];
+            V.Ps[i] = (float)ps;
+            V.Pd[i] = (float)(ps + l2dx);
+        } else {
+            V.z[i] = dxf;
+        }
     }
     for (int j = threadIdx.x; j < J; j += kCheckThreads) {
         const double v = V.v[j] + eps_abs * log(b[j]);
         V.v[j] = v;
         b[j] = 1.0;
         V.lv[j] = -v * i2;
-        V.w[j] = dyf;
+        if (V.online) {
+            const double qs = c1 * v - c2 * V.ny[j];
+            V.Qs[j] = (float)qs;
+            V.Qd[j] = (float)(qs + l2dy);
+        } else {
+            V.w[j] = dyf;
+        }
     }
 }
 
@@ -586,9 +602,32 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
         V.a[1][i] = 1.0;
         V.lu[i] = 0.0;
         V.lp[i] = log(V.p[i]);
-        V.z[i] = dxf;
         V.s[i] = 0.0;
+        if (V.online) {
+            const double ps = -ctrl->c2 * V.nx[i];
+            V.Ps[i] = (float)ps;
+            V.Pd[i] = (float)(ps - log2((double)I));
+        } else {
+            V.z[i] = dxf;
+        }
     }
+    if (V.online) {
+        for (long long i = I + threadIdx.x; i < V.n_pad_i; i += kCheckThreads) V.Ps[i] = V.Pd[i] = -INFINITY;
+        for (long long j = threadIdx.x; j < V.n_pad_j; j += kCheckThreads) {
+            if (j < J) {
+                const double qs = -ctrl->c2 * V.ny[j];
+                V.v[j] = 0.0;
+                V.b[0][j] = 1.0;
+                V.b[1][j] = 1.0;
+                V.lv[j] = 0.0;
+                V.t[j] = 0.0;
+                V.Qs[j] = (float)qs;
+                V.Qd[j] = (float)(qs - log2((double)J));
+            } else {
+                V.Qs[j] = V.Qd[j] = -INFINITY;
+            }
+        }
+    } else {
     for (int j = threadIdx.x; j < (int)ldw; j += kCheckThreads) {
         if (j < J) {
             V.v[j] = 0.0;
@@ -598,6 +637,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
             V.t[j] = 0.0;
         }
         V.w[j] = j < J ? dyf : 0.f;
+    }
     }
     sum = block_sum<kCheckThreads>(sum, red);
     if (threadIdx.x == 0) {
@@ -663,13 +703,17 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.sumK0_part = (double *)(base + o_k0);
     V.n_sumK0_part = n_k0_part;
     V.ldp = ldp;
+    V.online = 0;
+    V.nx = V.ny = nullptr;
+    V.Ps = V.Qs = V.Pd = V.Qd = nullptr;
+    V.n_pad_i = V.n_pad_j = 0;
     WOTB_CUDA(cudaMemsetAsync(V.tile_counters, 0, (size_t)n_col_tiles * 4 + 64, ctx->stream));
     WOTB_CUDA(cudaMemsetAsync(V.sumK0_part, 0, (size_t)n_k0_part * 8 + 64, ctx->stream));
     *out = V;
     return WOTB_OK;
 }
 
-int init_ctrl(const wotb_params *prm, int64_t I, int64_t J, SolveCtrl *h) {
+int init_ctrl(const wotb_params *prm, int64_t I, int64_t J, SolveCtrl *h, double median) {
     WOTB_REQUIRE(prm != nullptr, "params is NULL");
     WOTB_REQUIRE(I >= 1 && J >= 1 && I < (1ll << 31) && J < (1ll << 31), "I, J must be in [1, 2^31)");
     WOTB_REQUIRE(prm->solver == WOTB_SOLVER_DUALITY_GAP || prm->solver == WOTB_SOLVER_FIXED_ITERS, "unknown solver");
@@ -731,6 +775,9 @@ int init_ctrl(const wotb_params *prm, int64_t I, int64_t J, SolveCtrl *h) {
     h->alpha2 = h->lambda2 / (h->lambda2 + eps);
     h->inv_l1e = 1.0 / (h->lambda1 + eps);
     h->inv_l2e = 1.0 / (h->lambda2 + eps);
+    h->inv_median = 1.0 / median;
+    h->c1 = 1.4426950408889634 / eps;
+    h->c2 = h->c1 * h->inv_median;
     return WOTB_OK;
 }
 
@@ -830,7 +877,7 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
     WOTB_REQUIRE(((uintptr_t)C & 15) == 0, "C must be 16-byte aligned");
     memset(info, 0, sizeof(*info));
     SolveCtrl h;
-    WOTB_TRY(init_ctrl(prm, I, J, &h));
+    WOTB_TRY(init_ctrl(prm, I, J, &h, 1.0));
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
 
@@ -927,7 +974,7 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
     prm.epsilon = 0.05, prm.lambda1 = 1, prm.lambda2 = 50, prm.epsilon0 = 1, prm.tau = INFINITY, prm.tolerance = 1e-8;
     prm.max_iter = INFINITY, prm.batch_size = 5, prm.solver = WOTB_SOLVER_DUALITY_GAP;
     SolveCtrl h;
-    WOTB_TRY(init_ctrl(&prm, I, J, &h));
+    WOTB_TRY(init_ctrl(&prm, I, J, &h, 1.0));
     h.batch_iters = 1 << 30;
     h.need_build = 0;
     const int64_t ld = round_up(J, 32);
@@ -996,4 +1043,13 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
     return WOTB_OK;
 }
 
+}  // namespace wotb
+
+#include "online_pass.cuh"
+
+namespace wotb {
+int sinkhorn_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
+                    const double *G, const wotb_params *prm, double *f, double *g, double *rowsum, wotb_info *info) {
+    return sinkhorn_online_impl(ctx, x0, I, x1, J, d, median, G, prm, f, g, rowsum, info);
+}
 }  // namespace wotb

@@ -46,6 +46,9 @@ struct SolveCtrl {
     unsigned int grid_bar;  // arrival counter of the fused kernel's grid barrier (zeroed by k_build)
     unsigned long long seq;  // check kernels executed so far
     double eps_final, out_scale;
+    // ---- online kernel only --------------------------------------------------------------------
+    double inv_median;  // 1 / np.median(raw squared distances), ot_model.py:252
+    double c1, c2;      // log2(e)/eps and log2(e)/(eps*median): exponents are formed in base 2
 };
 
 // Pointers into the per-solve vector workspace (all device memory, fixed for the solve).
@@ -64,4 +67,10 @@ struct SolveVecs {
     double *sumK0_part;
     int n_sumK0_part;
     long long ldp;
+    // ---- online kernel only: exponent offsets, log2 domain (see online.cu) ----------------------
+    int online;
+    const double *nx, *ny;  // raw squared norms of the coordinates
+    float *Ps, *Qs;         // c1 u_i - c2 |x_i|^2 and c1 v_j - c2 |y_j|^2   (change on absorption / new eps)
+    float *Pd, *Qd;         // Ps + log2(a_i / I) and Qs + log2(b_j / J)      (change every half-step)
+    long long n_pad_i, n_pad_j;  // padded lengths; padding holds -inf so padded entries add exp2(-inf) = 0
 };
