@@ -170,6 +170,31 @@ int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, in
 int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J,
                                   int32_t d, const double *scale_host, double *C_host, double *median_out);
 
+/* ---- row-sharded online solve: one huge day-pair across GPUs (BASELINE.json configs[3]) ----------
+ * One process per GPU; every rank calls the same sequence.  x0, x1, G are the FULL arrays on every rank
+ * (device, float64); rank `shard` of `n_shards` computes a contiguous slice of 128-row tiles.  The solver
+ * state is replicated; two float64 vectors per iteration are summed across ranks by the CALLER (NCCL
+ * all-reduce on the context's stream) between the steps, through `exchange` (device, max(I,J) doubles):
+ *
+ *   per batch:      step BEGIN_A, all-reduce exchange[0:I], step BEGIN_B
+ *   per iteration:  step ROW, all-reduce exchange[0:I], step COL_PARTIAL, all-reduce exchange[0:J], step COL_FINISH
+ *   per batch end:  step GAP_ROWS, all-reduce exchange[0:I], step CHECK, then wotb_online_state() (syncs)
+ *   when done:      step FINAL_ROWS, all-reduce exchange[0:I]  -> row sums of the coupling
+ *
+ * Steps whose work is not due (batch finished early, tau stop, solver done) are no-ops on the device, so
+ * every rank issues the same collectives in the same order.  f [I], g [J] receive the potentials. */
+enum wotb_online_op {
+    WOTB_OP_BEGIN_A = 0, WOTB_OP_BEGIN_B = 1, WOTB_OP_ROW = 2, WOTB_OP_COL_PARTIAL = 3, WOTB_OP_COL_FINISH = 4,
+    WOTB_OP_GAP_ROWS = 5, WOTB_OP_CHECK = 6, WOTB_OP_FINAL_ROWS = 7
+};
+int wotb_online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d, double median,
+                     const double *G, const wotb_params *params, int32_t shard, int32_t n_shards, double *f, double *g,
+                     void **solve);
+int wotb_online_step(void *solve, int32_t op, double *exchange);
+int wotb_online_state(void *solve, wotb_info *info, int32_t *done);
+int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi);
+void wotb_online_close(void *solve);
+
 /* Measurement hook for bench.py: average device time (ms, CUDA events on the context's stream) of one
  * row-pass and one column-pass launch of the stored-K matvec kernels on an I x J kernel matrix. */
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,

@@ -1,0 +1,92 @@
+"""Host-side multi-process logic on CPU (gloo, world_size 2): unit sharding and the distributed form of
+compute_all_transport_maps.  The solver here is the float64 oracle plugged into OTModel.solver (the reference's
+de-facto plugin hook, ot_model.py:88-94) with caller-supplied cost matrices, so no GPU is touched."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_units_balances_and_keeps_order():
+    from wot_b200.parallel import shard_units
+    costs = [9, 1, 8, 2, 7, 3, 6, 4, 5]
+    parts = shard_units(costs, 3)
+    assert sorted(sum(parts, [])) == list(range(9))
+    loads = [sum(costs[k] for k in p) for p in parts]
+    assert max(loads) - min(loads) <= 2
+    assert all(p == sorted(p) for p in parts)
+    assert shard_units(costs, 1) == [list(range(9))]
+    assert shard_units([], 4) == [[], [], [], []]
+
+
+def _make_model():
+    from oracle import wot_oracle as orc
+    from wot_b200 import ot, synthetic
+    from wot_b200._anndata import AnnData
+    X, day, growth = synthetic.expression_matrix([30, 36, 33, 31], n_genes=40, seed=5)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    adata = AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])]))
+    model = ot.OTModel(adata, growth_iters=2, local_pca=0)
+    model.solver = lambda **kw: orc.optimal_transport_duality_gap(**kw)   # CPU plug-in solver
+    costs = []
+    for t0, t1 in ((0.0, 1.0), (1.0, 2.0), (2.0, 3.0)):
+        a, b = X[day == t0], X[day == t1]
+        costs.append(orc.compute_default_cost_matrix(a, b))
+    return model, costs
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wot_b200 import parallel
+        model, costs = _make_model()
+        done = parallel.compute_all_transport_maps(model, tmap_out=os.path.join(out_dir, "tm"),
+                                                   output_file_format="npz", cost_matrices=costs)
+        assert len(done) >= 1
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(300)
+def test_distributed_compute_all_transport_maps_matches_serial(tmp_path):
+    import torch.multiprocessing as mp
+    serial, dist_dir = tmp_path / "serial", tmp_path / "dist"
+    serial.mkdir()
+    dist_dir.mkdir()
+    model, costs = _make_model()
+    model.compute_all_transport_maps(tmap_out=str(serial / "tm"), output_file_format="npz", cost_matrices=costs)
+    mp.spawn(_worker, args=(2, _free_port(), str(dist_dir)), nprocs=2, join=True)
+    names = sorted(os.listdir(serial))
+    assert names == sorted(os.listdir(dist_dir))
+    assert "tm_g.txt" in names and "tm_0.0_1.0.npz" in names and len(names) == 4
+    for n in names:
+        if n.endswith(".npz"):
+            a, b = np.load(serial / n, allow_pickle=True), np.load(dist_dir / n, allow_pickle=True)
+            np.testing.assert_array_equal(a["X"], b["X"])
+            np.testing.assert_array_equal(a["obs_values"], b["obs_values"])
+        else:
+            assert (serial / n).read_text() == (dist_dir / n).read_text()
+
+
+def test_no_overwrite_skips_existing(tmp_path):
+    model, costs = _make_model()
+    out = str(tmp_path / "tm")
+    model.compute_all_transport_maps(tmap_out=out, output_file_format="npz", cost_matrices=costs)
+    stamp = os.path.getmtime(out + "_0.0_1.0.npz")
+    model.solver = None   # would raise if any pair were recomputed
+    model.compute_all_transport_maps(tmap_out=out, output_file_format="npz", cost_matrices=costs, overwrite=False)
+    assert os.path.getmtime(out + "_0.0_1.0.npz") == stamp

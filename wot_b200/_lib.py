@@ -68,6 +68,12 @@ SIGNATURES = {
     "wotb_transport_map_from_coords_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, C.POINTER(Params), _I32,
                                                       _P, _I32, _P, _P, _P, C.POINTER(_D), C.POINTER(Info)]),
     "wotb_default_cost_matrix_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _P, C.POINTER(_D)]),
+    "wotb_online_open": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _P, C.POINTER(Params), _I32, _I32, _P, _P,
+                                   C.POINTER(_P)]),
+    "wotb_online_step": (C.c_int, [_P, _I32, _P]),
+    "wotb_online_state": (C.c_int, [_P, C.POINTER(Info), C.POINTER(_I32)]),
+    "wotb_online_rows": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
+    "wotb_online_close": (None, [_P]),
     "wotb_bench_matvec_dev": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "wotb_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "wotb_pinned_free": (None, [_P]),

@@ -72,7 +72,14 @@ int cost_to_f32(wotb_ctx *, const double *, int64_t, int64_t, int64_t, float *, 
 int coupling(wotb_ctx *, const float *, int64_t, int64_t, int64_t, const double *, const double *, double, double,
              void *, int64_t, int, double *, cudaStream_t);
 int scale_into(wotb_ctx *, const double *, int64_t, int, const double *, double *);
-// online.cu
+// solver.cu (online_pass.cuh)
+struct OnlineSolve;
+int online_open(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
+                const wotb_params *, int, int, double *, double *, OnlineSolve **);
+int online_step(OnlineSolve *, int, double *);
+int online_state(OnlineSolve *, wotb_info *, int *);
+void online_rows(OnlineSolve *, int64_t *, int64_t *);
+void online_close(OnlineSolve *);
 int sinkhorn_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const wotb_params *, double *, double *, double *, wotb_info *);
 int coupling_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
@@ -433,6 +440,32 @@ int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t 
                                                           WOTB_F64);
                                    });
 }
+
+int wotb_online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d, double median,
+                     const double *G, const wotb_params *params, int32_t shard, int32_t n_shards, double *f, double *g,
+                     void **solve) {
+    OnlineSolve *S = nullptr;
+    WOTB_TRY(online_open(ctx, x0, I, x1, J, d, median, G, params, shard, n_shards, f, g, &S));
+    *solve = S;
+    return WOTB_OK;
+}
+
+int wotb_online_step(void *solve, int32_t op, double *exchange) { return online_step((OnlineSolve *)solve, op, exchange); }
+
+int wotb_online_state(void *solve, wotb_info *info, int32_t *done) {
+    int d = 0;
+    const int rc = online_state((OnlineSolve *)solve, info, &d);
+    if (done) *done = d;
+    return rc;
+}
+
+int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi) {
+    WOTB_REQUIRE(solve && row_lo && row_hi, "NULL argument");
+    online_rows((OnlineSolve *)solve, row_lo, row_hi);
+    return WOTB_OK;
+}
+
+void wotb_online_close(void *solve) { online_close((OnlineSolve *)solve); }
 
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
                           double *ms_fused) {

@@ -42,6 +42,9 @@ struct OnlineArgs {
     int seg_tiles;    // tiles per segment
     double *part;     // [nseg][out.ld] partial sums
     unsigned int *counters;  // one per out tile
+    int out_tile0;    // first out tile of this launch (row-sharded solves launch a slice of the tiles)
+    int in_tile0;     // first in tile that is reduced over
+    int in_ntiles;    // number of in tiles reduced over
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -63,10 +66,11 @@ __device__ __forceinline__ void cp_async_wait() {
 // mode 0: Sinkhorn half-step (row pass updates a, column pass updates b and closes the iteration)
 // mode 1: row sums only (duality-gap check)       mode 2: coupling row sums after the solve
 // mode 3: sum_ij exp(-C_ij/eps) row partials (final-stage `_K`, optimal_transport.py:121)
+// mode 4: half-step partial sums only, written to rowsum_out (row-sharded solves reduce them across GPUs)
 template <bool COLPASS>
 __global__ void __launch_bounds__(kOnThreads, 2)
     k_online_pass(OnlineArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
-    if (mode == 0) {
+    if (mode == 0 || mode == 4) {
         if (!iteration_active(ctrl)) return;
     } else if (mode == 1) {
         if (!gap_rows_wanted(ctrl)) return;
@@ -80,10 +84,10 @@ __global__ void __launch_bounds__(kOnThreads, 2)
     float *ys = xs + kOnChunk * kOnTile;                  // [2][kOnChunk][kOnTile] in-side tiles
     __shared__ int is_last;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int o0 = blockIdx.x * kOnTile;                  // first out entry of this CTA
-    const int t_begin = blockIdx.y * A.seg_tiles;
-    const int n_in_tiles = (A.in.n + kOnTile - 1) / kOnTile;
-    const int t_end = min(n_in_tiles, t_begin + A.seg_tiles);
+    const int out_tile = blockIdx.x + A.out_tile0;
+    const int o0 = out_tile * kOnTile;                    // first out entry of this CTA
+    const int t_begin = A.in_tile0 + blockIdx.y * A.seg_tiles;
+    const int t_end = min(A.in_tile0 + A.in_ntiles, t_begin + A.seg_tiles);
     const bool single_chunk = A.dp <= kOnChunk;
 
     float poff[8];
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(kOnThreads, 2)
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&A.counters[blockIdx.x], 1u);
+        const unsigned int ticket = atomicAdd(&A.counters[out_tile], 1u);
         is_last = ticket == gridDim.y - 1;
     }
     __syncthreads();
@@ -217,8 +221,10 @@ __global__ void __launch_bounds__(kOnThreads, 2)
                 V.s[o] = s;
             } else if (mode == 2) {
                 rowsum_out[o] = V.a[cur][o] * s * (ctrl->out_scale * (double)J);
-            } else {
+            } else if (mode == 3) {
                 V.sumK0_part[o] = s;
+            } else {
+                rowsum_out[o] = s;
             }
         }
     }
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(kOnThreads, 2)
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        A.counters[blockIdx.x] = 0;
+        A.counters[out_tile] = 0;
         if (mode == 0 && COLPASS) {
             const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
             if (ticket == gridDim.x - 1) {
@@ -361,10 +367,12 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
     row.out = {XT, ldi, V.Ps, (int)I};
     row.in = {YT, ldj, V.Qd, (int)J};
     row.dp = dp, row.nseg = nseg_row, row.seg_tiles = seg_tiles_row, row.part = part, row.counters = cnt_i;
+    row.out_tile0 = 0, row.in_tile0 = 0, row.in_ntiles = tiles_j;
     OnlineArgs col;  // reduce over i, one result per j
     col.out = {YT, ldj, V.Qs, (int)J};
     col.in = {XT, ldi, V.Pd, (int)I};
     col.dp = dp, col.nseg = nseg_col, col.seg_tiles = seg_tiles_col, col.part = part, col.counters = cnt_j;
+    col.out_tile0 = 0, col.in_tile0 = 0, col.in_ntiles = tiles_i;
     OnlineArgs s0 = row;
     s0.out.off = P0;
     s0.in.off = Q0;
@@ -409,6 +417,295 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
     fill_info(h, info);
     info->gpu_ms = ms;
     if (h.status == WOTB_STATUS_NAN) {
+        set_error("Overflow encountered in duality gap computation, please report this incident");
+        return WOTB_ERR_NAN_GAP;
+    }
+    return WOTB_OK;
+}
+
+// =================================================================================================
+// Row-sharded online solve (BASELINE.json configs[3]: one 100k x 100k pair on 2/4/8 GPUs).
+//
+// Every rank holds all coordinates (O((I+J) d), a few MB) and the full O(I+J) solver state, replicated;
+// it computes the row half-step for its slice of row tiles and the partial column sums over the same
+// slice.  Two exchanges per iteration, both a SUM all-reduce of one float64 vector (the caller runs them
+// with NCCL on the context's stream): the a-slices (zeros outside the slice, so the sum is an exact
+// all-gather) and the partial column sums.  Because the state is replicated, the convergence checks and
+// the whole state machine (k_check) run unchanged and identically on every rank: no further collective.
+// =================================================================================================
+__global__ void k_export_slice(const double *__restrict__ src, double *__restrict__ dst, int n, int lo, int hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (i >= lo && i < hi) ? src[i] : 0.0;
+}
+
+__global__ void k_export_a_slice(SolveVecs V, SolveCtrl *ctrl, double *__restrict__ dst, int lo, int hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *a = V.a[ctrl->cur ^ 1];
+    if (i < ctrl->I) dst[i] = (i >= lo && i < hi) ? a[i] : 0.0;
+}
+
+__global__ void k_import_a(SolveVecs V, SolveCtrl *ctrl, const double *__restrict__ src) {
+    if (!iteration_active(ctrl)) return;
+    const int I = ctrl->I;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double vmax = 0.0;
+    if (i < I) {
+        const double a = src[i];
+        V.a[ctrl->cur ^ 1][i] = a;
+        V.Pd[i] = (float)(ctrl->c1 * V.u[i] - ctrl->c2 * V.nx[i] + log2(a) - log2((double)I));
+        vmax = fabs(a);
+    }
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+}
+
+__global__ void k_import_vec(SolveCtrl *ctrl, const double *__restrict__ src, double *__restrict__ dst, int n,
+                             int what) {
+    // what 1: row sums for the gap check, 3: S0 row partials
+    if (what == 1 && !gap_rows_wanted(ctrl)) return;
+    if (what == 3 && (ctrl->done || !ctrl->need_build || ctrl->stage != WOTB_N_STAGES - 1)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+__global__ void k_online_col_finish(SolveVecs V, SolveCtrl *ctrl, const double *__restrict__ t_all) {
+    if (!iteration_active(ctrl)) return;
+    const int J = ctrl->J;
+    const int cur = ctrl->cur;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double vmax = 0.0;
+    if (j < J) {
+        const double t = t_all[j];
+        const double b = scaling_update(ctrl->lq, t, ctrl->alpha2, V.lv[j]);
+        V.b[cur ^ 1][j] = b;
+        V.t[j] = t;
+        V.Qd[j] = (float)(ctrl->c1 * V.v[j] - ctrl->c2 * V.ny[j] + log2(b) - log2((double)J));
+        vmax = fabs(b);
+    }
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            ctrl->col_tiles_done = 0;
+            close_iteration(ctrl);
+        }
+    }
+}
+
+struct OnlineSolve {
+    wotb_ctx *ctx;
+    int64_t I, J;
+    int d, dp;
+    int64_t ldi, ldj;
+    const double *x0, *x1;
+    float *XT, *YT, *P0, *Q0;
+    SolveVecs V;
+    SolveCtrl *d_ctrl;
+    SolveCtrl h;
+    OnlineArgs row, col, s0;
+    dim3 grid_row, grid_col;
+    int row_lo, row_hi;  // rows of this shard
+    size_t smem;
+    int64_t launches;
+};
+
+int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
+                const double *G, const wotb_params *prm, int shard, int n_shards, double *f, double *g,
+                OnlineSolve **out) {
+    WOTB_REQUIRE(ctx && x0 && x1 && G && f && g && out, "NULL argument");
+    WOTB_REQUIRE(d >= 1 && median > 0, "d must be >= 1 and the median positive");
+    WOTB_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards, "bad shard index");
+    OnlineSolve *S = new OnlineSolve();
+    S->ctx = ctx, S->I = I, S->J = J, S->d = d, S->x0 = x0, S->x1 = x1, S->launches = 0;
+    int rc = init_ctrl(prm, I, J, &S->h, median);
+    if (rc != WOTB_OK) {
+        delete S;
+        return rc;
+    }
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t ldi = round_up(I, kOnTile), ldj = round_up(J, kOnTile);
+    const int dp = (int)round_up(d, 4);
+    S->ldi = ldi, S->ldj = ldj, S->dp = dp;
+    const int tiles_i = (int)(ldi / kOnTile), tiles_j = (int)(ldj / kOnTile);
+    // contiguous slices of row tiles, as even as possible
+    const int t_lo = (int)((int64_t)tiles_i * shard / n_shards), t_hi = (int)((int64_t)tiles_i * (shard + 1) / n_shards);
+    const int my_tiles = t_hi - t_lo;
+    S->row_lo = t_lo * kOnTile;
+    S->row_hi = (int)(t_hi * (int64_t)kOnTile < I ? t_hi * (int64_t)kOnTile : I);
+    auto segs = [&](int out_tiles, int in_tiles, int *seg_tiles) {
+        if (out_tiles < 1) out_tiles = 1;
+        if (in_tiles < 1) in_tiles = 1;
+        int nseg = (int)cdiv((int64_t)ctx->sm_count * 2, out_tiles);
+        if (nseg > in_tiles) nseg = in_tiles;
+        if (nseg < 1) nseg = 1;
+        *seg_tiles = (int)cdiv(in_tiles, nseg);
+        return (int)cdiv(in_tiles, *seg_tiles);
+    };
+    int seg_tiles_row = 0, seg_tiles_col = 0;
+    const int nseg_row = segs(my_tiles, tiles_j, &seg_tiles_row);
+    const int nseg_col = segs(tiles_j, my_tiles, &seg_tiles_col);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) / 256 * 256;
+        return at;
+    };
+    const size_t o_xt = take((size_t)dp * ldi * 4), o_yt = take((size_t)dp * ldj * 4);
+    const size_t o_nx = take((size_t)I * 8), o_ny = take((size_t)J * 8);
+    const size_t o_ps = take((size_t)ldi * 4), o_qs = take((size_t)ldj * 4);
+    const size_t o_pd = take((size_t)ldi * 4), o_qd = take((size_t)ldj * 4);
+    const size_t o_p0 = take((size_t)ldi * 4), o_q0 = take((size_t)ldj * 4);
+    const size_t o_part = take((size_t)(nseg_row > nseg_col ? nseg_row : nseg_col) * (ldi > ldj ? ldi : ldj) * 8);
+    const size_t o_cnt = take((size_t)(tiles_i + tiles_j) * 4 + 64);
+    WOTB_TRY(ctx->onl.reserve(off));
+    char *ob = ctx->onl.as<char>();
+    S->XT = (float *)(ob + o_xt), S->YT = (float *)(ob + o_yt);
+    double *nx = (double *)(ob + o_nx), *ny = (double *)(ob + o_ny);
+    S->P0 = (float *)(ob + o_p0), S->Q0 = (float *)(ob + o_q0);
+    double *part = (double *)(ob + o_part);
+    unsigned int *cnt_i = (unsigned int *)(ob + o_cnt), *cnt_j = cnt_i + tiles_i;
+    WOTB_CUDA(cudaMemsetAsync(cnt_i, 0, (size_t)(tiles_i + tiles_j) * 4, st));
+    WOTB_TRY(carve_vectors(ctx, I, J, round_up(J, 32), 1, 1, (int)I, G, f, g, &S->V));
+    SolveVecs &V = S->V;
+    V.online = 1;
+    V.nx = nx, V.ny = ny;
+    V.Ps = (float *)(ob + o_ps), V.Qs = (float *)(ob + o_qs);
+    V.Pd = (float *)(ob + o_pd), V.Qd = (float *)(ob + o_qd);
+    V.n_pad_i = ldi, V.n_pad_j = ldj;
+    WOTB_TRY(ctx->ctrl.reserve(sizeof(SolveCtrl)));
+    S->d_ctrl = ctx->ctrl.as<SolveCtrl>();
+    WOTB_TRY(ctx->status.reserve(256));
+    *ctx->status.as<int>() = 0;
+    k_sqnorms<<<(unsigned)cdiv(I, 256), 256, 0, st>>>(x0, (int)I, d, nx);
+    k_sqnorms<<<(unsigned)cdiv(J, 256), 256, 0, st>>>(x1, (int)J, d, ny);
+    WOTB_CUDA(cudaMemcpyAsync(S->d_ctrl, &S->h, sizeof(S->h), cudaMemcpyHostToDevice, st));
+    launch_init(ctx, V, S->d_ctrl, round_up(J, 32));
+    S->smem = (size_t)3 * kOnChunk * kOnTile * 4;
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
+    S->row.out = {S->XT, ldi, V.Ps, (int)I};
+    S->row.in = {S->YT, ldj, V.Qd, (int)J};
+    S->row.dp = dp, S->row.nseg = nseg_row, S->row.seg_tiles = seg_tiles_row, S->row.part = part;
+    S->row.counters = cnt_i, S->row.out_tile0 = t_lo, S->row.in_tile0 = 0, S->row.in_ntiles = tiles_j;
+    S->col.out = {S->YT, ldj, V.Qs, (int)J};
+    S->col.in = {S->XT, ldi, V.Pd, (int)I};
+    S->col.dp = dp, S->col.nseg = nseg_col, S->col.seg_tiles = seg_tiles_col, S->col.part = part;
+    S->col.counters = cnt_j, S->col.out_tile0 = 0, S->col.in_tile0 = t_lo, S->col.in_ntiles = my_tiles;
+    S->s0 = S->row;
+    S->s0.out.off = S->P0;
+    S->s0.in.off = S->Q0;
+    S->grid_row = dim3(my_tiles > 0 ? my_tiles : 1, nseg_row);
+    S->grid_col = dim3(tiles_j, nseg_col);
+    S->launches = 3;
+    WOTB_CUDA(cudaGetLastError());
+    *out = S;
+    return WOTB_OK;
+}
+
+enum OnlineOp {
+    kOpBeginA = 0,      // rescale coordinates if eps changed; final stage: S0 row partials of the slice -> exch[I]
+    kOpBeginB = 1,      // take the reduced S0 partials; mark the kernel as current
+    kOpRow = 2,         // row half-step on the slice; a slice -> exch[I]
+    kOpColPartial = 3,  // take the gathered a; partial column sums over the slice -> exch[J]
+    kOpColFinish = 4,   // take the reduced column sums; b update; close the iteration
+    kOpGapRows = 5,     // final stage: row sums of the slice for the duality gap -> exch[I]
+    kOpCheck = 6,       // take the gathered row sums; run the state machine
+    kOpFinalRows = 7    // coupling row sums of the slice -> exch[I]
+};
+
+int online_step(OnlineSolve *S, int op, double *exch) {
+    WOTB_REQUIRE(S != nullptr, "solve handle is NULL");
+    wotb_ctx *ctx = S->ctx;
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const SolveVecs &V = S->V;
+    SolveCtrl *c = S->d_ctrl;
+    const int I = (int)S->I, J = (int)S->J;
+    const unsigned bi = (unsigned)cdiv(I, 256), bj = (unsigned)cdiv(J, 256);
+    const bool have_rows = S->row_hi > S->row_lo;
+    const bool dg = S->h.solver == WOTB_SOLVER_DUALITY_GAP;
+    switch (op) {
+        case kOpBeginA:
+            k_online_scale<<<(unsigned)cdiv((int64_t)S->dp * S->ldi, 256), 256, 0, st>>>(S->x0, I, S->d, S->XT, S->ldi,
+                                                                                         S->dp, c, 0);
+            k_online_scale<<<(unsigned)cdiv((int64_t)S->dp * S->ldj, 256), 256, 0, st>>>(S->x1, J, S->d, S->YT, S->ldj,
+                                                                                         S->dp, c, 0);
+            S->launches += 2;
+            if (dg) {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                k_online_s0_offsets<<<(unsigned)cdiv(S->ldi > S->ldj ? S->ldi : S->ldj, 256), 256, 0, st>>>(V, c, S->P0,
+                                                                                                            S->Q0);
+                if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->s0, V, c, 3, nullptr);
+                k_export_slice<<<bi, 256, 0, st>>>(V.sumK0_part, exch, I, S->row_lo, S->row_hi);
+                S->launches += 3;
+            }
+            break;
+        case kOpBeginB:
+            if (dg) {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                k_import_vec<<<bi, 256, 0, st>>>(c, exch, V.sumK0_part, I, 3);
+            }
+            k_online_built<<<1, 32, 0, st>>>(c);
+            S->launches += 2;
+            break;
+        case kOpRow:
+            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+            if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 0, nullptr);
+            k_export_a_slice<<<bi, 256, 0, st>>>(V, c, exch, S->row_lo, S->row_hi);
+            S->launches += 2;
+            break;
+        case kOpColPartial:
+            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+            k_import_a<<<bi, 256, 0, st>>>(V, c, exch);
+            WOTB_CUDA(cudaMemsetAsync(exch, 0, (size_t)J * 8, st));
+            if (have_rows) k_online_pass<true><<<S->grid_col, kOnThreads, S->smem, st>>>(S->col, V, c, 4, exch);
+            S->launches += 2;
+            break;
+        case kOpColFinish:
+            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+            k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch);
+            S->launches += 1;
+            break;
+        case kOpGapRows:
+            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+            if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 1, nullptr);
+            k_export_slice<<<bi, 256, 0, st>>>(V.s, exch, I, S->row_lo, S->row_hi);
+            S->launches += 2;
+            break;
+        case kOpCheck:
+            if (dg) {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                k_import_vec<<<bi, 256, 0, st>>>(c, exch, V.s, I, 1);
+            }
+            launch_check(ctx, V, c, ctx->status.as<int>());
+            S->launches += 2;
+            break;
+        case kOpFinalRows:
+            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+            WOTB_CUDA(cudaMemsetAsync(exch, 0, (size_t)I * 8, st));
+            if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 2, exch);
+            S->launches += 1;
+            break;
+        default:
+            WOTB_REQUIRE(false, "unknown online step");
+    }
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+int online_state(OnlineSolve *S, wotb_info *info, int *done) {
+    WOTB_REQUIRE(S && info && done, "NULL argument");
+    WOTB_CUDA(cudaMemcpyAsync(&S->h, S->d_ctrl, sizeof(S->h), cudaMemcpyDeviceToHost, S->ctx->stream));
+    WOTB_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    fill_info(S->h, info);
+    info->launches = S->launches;
+    *done = S->h.done;
+    if (S->h.done && S->h.status == WOTB_STATUS_NAN) {
         set_error("Overflow encountered in duality gap computation, please report this incident");
         return WOTB_ERR_NAN_GAP;
     }

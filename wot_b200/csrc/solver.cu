@@ -1052,4 +1052,9 @@ int sinkhorn_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1
                     const double *G, const wotb_params *prm, double *f, double *g, double *rowsum, wotb_info *info) {
     return sinkhorn_online_impl(ctx, x0, I, x1, J, d, median, G, prm, f, g, rowsum, info);
 }
+void online_rows(OnlineSolve *S, int64_t *lo, int64_t *hi) {
+    *lo = S->row_lo;
+    *hi = S->row_hi;
+}
+void online_close(OnlineSolve *S) { delete S; }
 }  // namespace wotb

@@ -1,0 +1,220 @@
+"""Multi-GPU execution of the transport-map path: one process per GPU, torch.distributed for plumbing.
+
+Two partitionings (BASELINE.json north_star):
+
+1. Independent day-pairs (and parameter settings) share nothing: `shard_units` deals them to ranks,
+   longest first; `compute_all_transport_maps` runs a rank's pairs and gathers the learned-growth tables so
+   the outputs (file names, `{prefix}_g.txt` row order, --no_overwrite skipping) equal the serial loop of
+   the reference (ot_model.py:182-201).  No collective sits on the data path.
+
+2. One very large pair is row-sharded: `sharded_online_solve` drives the stepping entry points of the
+   library (wotb_online_*): each rank computes its slice of rows with the online kernel and the ranks
+   exchange two float64 vectors per Sinkhorn iteration with an NCCL all-reduce over NVLink.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. independent units
+# ------------------------------------------------------------------------------------------------
+def shard_units(costs, world_size):
+    """Longest-processing-time-first assignment.  costs[k] ~ I*J*expected_iterations of unit k.
+    Returns a list (per rank) of unit indices; each rank's list keeps the original order."""
+    loads = [0.0] * world_size
+    owner = [0] * len(costs)
+    for k in sorted(range(len(costs)), key=lambda q: (-costs[q], q)):
+        r = min(range(world_size), key=lambda q: (loads[q], q))
+        owner[k] = r
+        loads[r] += float(costs[k])
+    return [[k for k in range(len(costs)) if owner[k] == r] for r in range(world_size)]
+
+
+def _rank_world(group=None):
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(group), dist.get_world_size(group)
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_file_format="h5ad",
+                               cost_matrices=None, group=None):
+    """Distributed form of OTModel.compute_all_transport_maps (ot_model.py:124-201, covariate-free case).
+
+    Every rank calls it with the same model.  Day-pairs are dealt to ranks by cell-count product; each rank
+    writes its own '{prefix}_{t0}_{t1}.{fmt}' files; rank 0 writes '{prefix}_g.txt' with the rows of all
+    pairs in day-pair order, exactly as the serial loop concatenates them."""
+    import pandas as pd
+    import torch.distributed as dist
+
+    from . import io as _io
+
+    rank, world = _rank_world(group)
+    tmap_dir, tmap_prefix = os.path.split(tmap_out) if tmap_out is not None else (None, None)
+    tmap_prefix = tmap_prefix or "tmaps"
+    tmap_dir = tmap_dir or "."
+    os.makedirs(tmap_dir, exist_ok=True)
+    day_pairs = model.day_pairs
+    if day_pairs is None or len(day_pairs) == 0:
+        t = model.timepoints
+        day_pairs = [(t[k], t[k + 1]) for k in range(len(t) - 1)]
+    else:
+        day_pairs = list(day_pairs)
+    if cost_matrices is None:
+        cost_matrices = [None] * len(day_pairs)
+    files = [_io.check_file_extension(os.path.join(tmap_dir, tmap_prefix + "_{}_{}".format(*p)), output_file_format)
+             for p in day_pairs]
+    todo = [k for k in range(len(day_pairs)) if overwrite or not os.path.exists(files[k])]  # skip before dispatch
+    days = model.matrix.obs[model.day_field]
+    counts = days.value_counts()
+    costs = [float(counts.get(day_pairs[k][0], 0)) * float(counts.get(day_pairs[k][1], 0)) for k in todo]
+    mine = [todo[q] for q in shard_units(costs, world)[rank]]
+    keep_growth = model.ot_config.get("growth_iters", 1) > 1
+    frames = {}
+    for k in mine:
+        tmap = model.compute_transport_map(*day_pairs[k], cost_matrix=cost_matrices[k])
+        if tmap is None:
+            continue
+        _io.write_dataset(tmap, files[k], output_format=output_file_format)
+        if keep_growth:
+            frames[k] = tmap.obs
+    if keep_growth:
+        gathered = [frames]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, frames, group=group)
+        if rank == 0:
+            merged = {}
+            for part in gathered:
+                merged.update(part)
+            if merged:
+                pd.concat([merged[k] for k in sorted(merged)]).to_csv(
+                    os.path.join(tmap_dir, tmap_prefix + "_g.txt"), sep="\t", index_label="id")
+    if world > 1:
+        dist.barrier(group=group)
+    return [day_pairs[k] for k in mine]
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. one pair, rows sharded
+# ------------------------------------------------------------------------------------------------
+OP_BEGIN_A, OP_BEGIN_B, OP_ROW, OP_COL_PARTIAL, OP_COL_FINISH, OP_GAP_ROWS, OP_CHECK, OP_FINAL_ROWS = range(8)
+
+
+def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, **params):
+    """Solve one day-pair with its rows sharded over the ranks of `group` (online kernel, float64 state).
+
+    x0 [I,d], x1 [J,d], G [I]: the full arrays on every rank (NumPy or CUDA tensors).  Returns a dict with
+    f, g (replicated CUDA tensors), rowsum (replicated), rows=(lo, hi) of this rank, median, info.
+    With world_size 1 no collective is issued (the stepping path is then a plain single-GPU solve).
+    """
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+
+    rank, world = _rank_world(group)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    stream = stream or torch.cuda.current_stream(dev)
+    ctx = _lib.Context(device, stream.cuda_stream if stream.cuda_stream else None)
+    lib, h = ctx.lib, ctx.handle
+
+    def to_dev(a):
+        if isinstance(a, torch.Tensor):
+            return a.to(dev, torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+    with torch.cuda.stream(stream):
+        X0, X1, Gd = to_dev(x0), to_dev(x1), to_dev(G)
+        n_i, n_j, d = X0.shape[0], X1.shape[0], X0.shape[1]
+        P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        median = params.pop("median", None)
+        if median is None:
+            # every rank runs the exact select on the full problem (6 recompute passes; cheap next to the
+            # solve) so the value is bit-identical everywhere without a collective
+            med = C.c_double()
+            _lib.check(lib.wotb_cost_median_dev(h, P(X0), n_i, P(X1), n_j, d, None, C.byref(med)))
+            median = med.value
+        solver = params.pop("solver", _lib.SOLVER_DUALITY_GAP)
+        prm = _lib.make_params(solver=solver, kernel=_lib.KERNEL_ONLINE, **params)
+        f = torch.empty(n_i, dtype=torch.float64, device=dev)
+        g = torch.empty(n_j, dtype=torch.float64, device=dev)
+        exch = torch.zeros(max(n_i, n_j), dtype=torch.float64, device=dev)
+        solve = C.c_void_p()
+        _lib.check(lib.wotb_online_open(h, P(X0), n_i, P(X1), n_j, d, median, P(Gd), C.byref(prm), rank, world, P(f),
+                                        P(g), C.byref(solve)))
+
+        def step(op):
+            _lib.check(lib.wotb_online_step(solve, op, P(exch)))
+
+        def reduce(n):
+            if world > 1:
+                dist.all_reduce(exch[:n], op=dist.ReduceOp.SUM, group=group)
+
+        slots = 5 if solver == _lib.SOLVER_DUALITY_GAP else 10
+        info, done = _lib.Info(), C.c_int32(0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record(stream)
+        try:
+            while True:
+                step(OP_BEGIN_A)
+                if solver == _lib.SOLVER_DUALITY_GAP:
+                    reduce(n_i)
+                step(OP_BEGIN_B)
+                for _ in range(slots):
+                    step(OP_ROW)
+                    reduce(n_i)
+                    step(OP_COL_PARTIAL)
+                    reduce(n_j)
+                    step(OP_COL_FINISH)
+                if solver == _lib.SOLVER_DUALITY_GAP:
+                    step(OP_GAP_ROWS)
+                    reduce(n_i)
+                step(OP_CHECK)
+                _lib.check(lib.wotb_online_state(solve, C.byref(info), C.byref(done)))
+                if done.value:
+                    break
+            step(OP_FINAL_ROWS)
+            reduce(n_i)
+            rowsum = exch[:n_i].clone()
+            ev[1].record(stream)
+            ev[1].synchronize()
+            lo, hi = C.c_int64(), C.c_int64()
+            _lib.check(lib.wotb_online_rows(solve, C.byref(lo), C.byref(hi)))
+        finally:
+            lib.wotb_online_close(solve)
+        out_info = info.as_dict()
+        out_info["gpu_ms"] = ev[0].elapsed_time(ev[1])
+    return {"f": f, "g": g, "rowsum": rowsum, "rows": (lo.value, hi.value), "median": median, "info": out_info,
+            "ctx": ctx, "coords": (X0, X1)}
+
+
+def local_coupling_rows(result, out_dtype=np.float64):
+    """Materialise this rank's rows of the coupling of a sharded solve (host ndarray [hi-lo, J])."""
+    import torch
+
+    from . import _lib
+    ctx = result["ctx"]
+    X0, X1 = result["coords"]
+    lo, hi = result["rows"]
+    n_j, d = X1.shape[0], X1.shape[1]
+    info = result["info"]
+    tdt = torch.float64 if np.dtype(out_dtype) == np.float64 else torch.float32
+    out = torch.empty((hi - lo, n_j), dtype=tdt, device=X0.device)
+    if hi > lo:
+        P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        _lib.check(ctx.lib.wotb_coupling_online_dev(
+            ctx.handle, C.c_void_p(X0.data_ptr() + lo * d * 8), hi - lo, P(X1), n_j, d, result["median"],
+            C.c_void_p(result["f"].data_ptr() + lo * 8), P(result["g"]), info["eps_final"], info["out_scale"], P(out),
+            n_j, _lib.F64 if tdt == torch.float64 else _lib.F32, None))
+    return out.cpu().numpy()
