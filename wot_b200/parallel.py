@@ -125,8 +125,10 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         device = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
-    stream = stream or torch.cuda.current_stream(dev)
-    ctx = _lib.Context(device, stream.cuda_stream if stream.cuda_stream else None)
+    # the library's kernels and the NCCL all-reduces must be ordered on ONE stream: a dedicated torch stream
+    # that is made current while the solve runs (the legacy default stream has no usable handle)
+    stream = stream or torch.cuda.Stream(dev)
+    ctx = _lib.Context(device, stream.cuda_stream)
     lib, h = ctx.lib, ctx.handle
 
     def to_dev(a):
