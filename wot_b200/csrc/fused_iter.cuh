@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kFuseThreads, 1)
     for (int it = 0; it < max_iters; ++it) {
         if (it > 0 && (vc->done || vc->stop != 0 || vc->batch_done >= vc->batch_iters)) break;
         const int cur = vc->cur;
+        const bool first_of_batch = vc->batch_done == 0;
         // =========================== phase A: one sweep over this CTA's rows ====================
         if (wid == kFuseComputeWarps + 1) {
             // ---------------- TMA producer ------------------------------------------------------
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kFuseThreads, 1)
                 if (lane == 0) {
                     const double a = scaling_update(lp, part_sum, alpha1, lu);
                     a_out[row] = a;
+                    if (first_of_batch) V.sfirst[row] = part_sum;
                     zs[s] = (float)(a * dx);
                     amax = fmax(amax, fabs(a));
                     mbar_arrive(&zready[s]);

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kOnThreads, 2)
                     const double a = scaling_update(V.lp[o], s, ctrl->alpha1, V.lu[o]);
                     V.a[cur ^ 1][o] = a;
                     V.s[o] = s;
+                    if (ctrl->batch_done == 0) V.sfirst[o] = s;
                     V.Pd[o] = (float)(ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
                     vmax = fabs(a);
                 } else {
@@ -345,6 +346,7 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
     V.Qd = (float *)(ob + o_qd);
     V.n_pad_i = ldi;
     V.n_pad_j = ldj;
+    V.rowsum = rowsum;
     WOTB_TRY(ctx->ctrl.reserve(sizeof(SolveCtrl)));
     SolveCtrl *d_ctrl = ctx->ctrl.as<SolveCtrl>();
     WOTB_TRY(ctx->status.reserve(256));
@@ -392,18 +394,16 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
             k_online_pass<false><<<grid_row, kOnThreads, smem, st>>>(row, V, d_ctrl, 0, nullptr);
             k_online_pass<true><<<grid_col, kOnThreads, smem, st>>>(col, V, d_ctrl, 0, nullptr);
         }
-        if (h.solver == WOTB_SOLVER_DUALITY_GAP)
-            k_online_pass<false><<<grid_row, kOnThreads, smem, st>>>(row, V, d_ctrl, 1, nullptr);
         launch_check(ctx, V, d_ctrl, host_done);
     };
-    const int per_seq = 4 + 2 * slots + (h.solver == WOTB_SOLVER_DUALITY_GAP ? 3 : 0);
+    const int per_seq = 4 + 2 * slots + (h.solver == WOTB_SOLVER_DUALITY_GAP ? 2 : 0);
     info->launches = 3;
     int rc = pump(ctx, prm->use_graph != 0, per_seq, 2 * slots, sequence, info);
     if (rc != WOTB_OK) return rc;
 
     WOTB_CUDA(cudaMemcpyAsync(&h, d_ctrl, sizeof(h), cudaMemcpyDeviceToHost, st));
     WOTB_CUDA(cudaStreamSynchronize(st));
-    if (rowsum) {
+    if (rowsum && !h.rowsum_ready) {
         // offsets and scaled coordinates are consistent with (u, v, a, b) even after a trailing absorption
         // (absorb() refreshes them; the coordinate scale only depends on eps)
         k_online_pass<false><<<grid_row, kOnThreads, smem, st>>>(row, V, d_ctrl, 2, rowsum);
@@ -438,10 +438,16 @@ __global__ void k_export_slice(const double *__restrict__ src, double *__restric
     if (i < n) dst[i] = (i >= lo && i < hi) ? src[i] : 0.0;
 }
 
+// a-slice into dst[0:I], row-sum slice into dst[I:2I] (the row sums feed the lazy duality-gap check)
 __global__ void k_export_a_slice(SolveVecs V, SolveCtrl *ctrl, double *__restrict__ dst, int lo, int hi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int I = ctrl->I;
     const double *a = V.a[ctrl->cur ^ 1];
-    if (i < ctrl->I) dst[i] = (i >= lo && i < hi) ? a[i] : 0.0;
+    if (i < I) {
+        const bool mine = i >= lo && i < hi;
+        dst[i] = mine ? a[i] : 0.0;
+        dst[I + i] = mine ? V.s[i] : 0.0;
+    }
 }
 
 __global__ void k_import_a(SolveVecs V, SolveCtrl *ctrl, const double *__restrict__ src) {
@@ -452,6 +458,7 @@ __global__ void k_import_a(SolveVecs V, SolveCtrl *ctrl, const double *__restric
     if (i < I) {
         const double a = src[i];
         V.a[ctrl->cur ^ 1][i] = a;
+        if (ctrl->batch_done == 0) V.sfirst[i] = src[I + i];
         V.Pd[i] = (float)(ctrl->c1 * V.u[i] - ctrl->c2 * V.nx[i] + log2(a) - log2((double)I));
         vmax = fabs(a);
     }
@@ -577,6 +584,7 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     V.Ps = (float *)(ob + o_ps), V.Qs = (float *)(ob + o_qs);
     V.Pd = (float *)(ob + o_pd), V.Qd = (float *)(ob + o_qd);
     V.n_pad_i = ldi, V.n_pad_j = ldj;
+    V.rowsum = V.r;  // row sums of a snapshot finish land here (V.r is free once the solve is done)
     WOTB_TRY(ctx->ctrl.reserve(sizeof(SolveCtrl)));
     S->d_ctrl = ctx->ctrl.as<SolveCtrl>();
     WOTB_TRY(ctx->status.reserve(256));
@@ -671,24 +679,20 @@ int online_step(OnlineSolve *S, int op, double *exch) {
             k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch);
             S->launches += 1;
             break;
-        case kOpGapRows:
-            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 1, nullptr);
-            k_export_slice<<<bi, 256, 0, st>>>(V.s, exch, I, S->row_lo, S->row_hi);
-            S->launches += 2;
+        case kOpGapRows:  // kept for ABI stability: the row sums of the gap now ride on kOpRow (lazy check)
             break;
         case kOpCheck:
-            if (dg) {
-                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-                k_import_vec<<<bi, 256, 0, st>>>(c, exch, V.s, I, 1);
-            }
             launch_check(ctx, V, c, ctx->status.as<int>());
-            S->launches += 2;
+            S->launches += 1;
             break;
         case kOpFinalRows:
             WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            WOTB_CUDA(cudaMemsetAsync(exch, 0, (size_t)I * 8, st));
-            if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 2, exch);
+            if (S->h.rowsum_ready) {  // converged from a snapshot: its row sums were written by the check
+                k_export_slice<<<bi, 256, 0, st>>>(V.rowsum, exch, I, S->row_lo, S->row_hi);
+            } else {
+                WOTB_CUDA(cudaMemsetAsync(exch, 0, (size_t)I * 8, st));
+                if (have_rows) k_online_pass<false><<<S->grid_row, kOnThreads, S->smem, st>>>(S->row, V, c, 2, exch);
+            }
             S->launches += 1;
             break;
         default:

@@ -84,6 +84,18 @@ __device__ __forceinline__ bool gap_rows_wanted(const SolveCtrl *c) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kBuildThreads = 256;
 
+// exp2(y) for a float64 exponent, rounded to fp32: the integer part is split off exactly in float64, the
+// fraction (|r| <= 0.5, exact in fp32 to 3e-8) goes through MUFU.EX2 (relative error <= 2^-22), and the
+// result is scaled by 2^n.  Six FP64 instructions per entry instead of the ~45 of exp(double): K builds
+// become HBM-bound.  Underflow flushes to zero (entries below 1e-38 are 26 orders below the parity floor).
+__device__ __forceinline__ float exp_to_f32(double y) {
+    y = fmin(fmax(y, -300.0), 300.0);
+    const double n = rint(y);
+    float p;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"((float)(y - n)));
+    return scalbnf(p, (int)n);
+}
+
 __global__ void __launch_bounds__(kBuildThreads) k_build(const float *__restrict__ C, long long ldc,
                                                          float *__restrict__ K, long long ld, SolveVecs V,
                                                          SolveCtrl *ctrl) {
@@ -91,7 +103,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build(const float *__restrict
     if (ctrl->done || !ctrl->need_build) return;
     __shared__ double red[33];
     const int I = ctrl->I, J = ctrl->J;
-    const double inv_eps = 1.0 / ctrl->eps;
+    const double inv_eps_log2e = 1.4426950408889634 / ctrl->eps;
     const bool want_k0 = ctrl->solver == WOTB_SOLVER_DUALITY_GAP && ctrl->stage == WOTB_N_STAGES - 1;
     const int n4 = (int)(ld >> 2);
     double k0 = 0.0;
@@ -110,8 +122,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_build(const float *__restrict
                 for (int e = 0; e < 4; ++e) {
                     if (j + e < J) {
                         const double cij = (double)cc[e];
-                        kk[e] = (float)exp((ui - cij + __ldg(V.v + j + e)) * inv_eps);
-                        if (want_k0) k0 += exp(-cij * inv_eps);
+                        kk[e] = exp_to_f32((ui - cij + __ldg(V.v + j + e)) * inv_eps_log2e);
+                        if (want_k0) k0 += (double)exp_to_f32(-cij * inv_eps_log2e);
                     }
                 }
                 out = make_float4(kk[0], kk[1], kk[2], kk[3]);
@@ -144,6 +156,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row(const float *__restrict__ K
     }
     const int I = ctrl->I;
     const int cur = ctrl->cur;
+    const bool first_of_batch = ctrl->batch_done == 0;
     const double alpha1 = ctrl->alpha1;
     const double dx = 1.0 / (double)I;
     const double out_scale = ctrl->out_scale * (double)ctrl->J;
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(kRowThreads) k_row(const float *__restrict__ K
             if (mode == 0) {
                 const double a = scaling_update(V.lp[row], acc, alpha1, V.lu[row]);
                 a_out[row] = a;
-                V.s[row] = acc;
+                if (first_of_batch) V.sfirst[row] = acc;
                 V.z[row] = (float)(a * dx);
                 amax = fmax(amax, fabs(a));
             } else if (mode == 1) {
@@ -407,11 +420,80 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
     const double eps = c->eps;
     __syncthreads();
 
-    // 1. marginals of R = a K b, before any absorption (R is invariant under it; a and b are not)
+    // 0. Lazy duality gap (final stage).  primal/dual of the state at the previous batch end need the row
+    //    sums K (b dy) of THAT state, which is exactly what the first iteration of the batch that followed
+    //    it computed on its way (V.sfirst).  So the check of batch n is evaluated here, one batch late, from
+    //    the snapshot (f, g, column sums, a) taken then: no extra sweep over K per check.  If it converged,
+    //    the snapshot is the answer and the speculative batch is dropped (<= batch_size iterations per solve).
+    if (final_dg && c->snap_valid && (complete || (stop & 2))) {
+        const double l1 = c->lambda1, l2 = c->lambda2, qm = c->q;
+        const double dx = 1.0 / (double)I, dy = 1.0 / (double)J;
+        double kl1 = 0.0, kl2 = 0.0, fr = 0.0, gc = 0.0, sr = 0.0, c1 = 0.0, c2 = 0.0;
+        for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+            const double r = V.as[i] * V.sfirst[i] * (double)J, p = V.p[i];
+            const double f = V.fs[i];
+            const double x = r * dy;
+            V.r[i] = r;
+            kl1 += dx * (x * log(x / p) - x + p);
+            fr += f * r;
+            sr += r;
+            c1 += (p * dx) * (exp(-f / l1) - 1.0);
+        }
+        for (int j = threadIdx.x; j < J; j += kCheckThreads) {
+            const double cj = V.cs[j];
+            const double g = V.gs[j];
+            const double y = cj * dx;
+            kl2 += dy * (y * log(y / qm) - y + qm);
+            gc += g * cj;
+            c2 += (qm * dy) * (exp(-g / l2) - 1.0);
+        }
+        double k0 = 0.0;
+        for (int k = threadIdx.x; k < V.n_sumK0_part; k += kCheckThreads) k0 += V.sumK0_part[k];
+        kl1 = block_sum<kCheckThreads>(kl1, red);
+        kl2 = block_sum<kCheckThreads>(kl2, red);
+        fr = block_sum<kCheckThreads>(fr, red);
+        gc = block_sum<kCheckThreads>(gc, red);
+        sr = block_sum<kCheckThreads>(sr, red);
+        c1 = block_sum<kCheckThreads>(c1, red);
+        c2 = block_sum<kCheckThreads>(c2, red);
+        k0 = block_sum<kCheckThreads>(k0, red);
+        const double ij = (double)I * (double)J;
+        const double pri = l1 * kl1 + l2 * kl2 + (fr + gc - eps * sr + eps * k0) / ij;
+        const double dua = -l1 * c1 - l2 * c2 - eps * (sr - k0) / ij;
+        const double lazy_gap = (pri - dua) / fabs(pri);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            c->primal = pri;
+            c->dual = dua;
+            c->sumK0 = k0;
+            c->gap = lazy_gap;
+            c->batches[stage] += 1;
+            c->snap_valid = 0;
+        }
+        if (!(lazy_gap > c->tolerance)) {  // converged (or NaN, :129): return the snapshot
+            for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+                V.f[i] = V.fs[i];
+                if (V.rowsum) V.rowsum[i] = V.r[i] * dy;
+            }
+            for (int j = threadIdx.x; j < J; j += kCheckThreads) V.g[j] = V.gs[j];
+            if (threadIdx.x == 0) {
+                c->done = 1;
+                c->status = lazy_gap != lazy_gap ? WOTB_STATUS_NAN : WOTB_STATUS_CONVERGED;
+                c->eps_final = eps;
+                c->out_scale = dy;
+                c->iter = c->snap_iter;
+                c->rowsum_ready = V.rowsum != nullptr;
+            }
+            publish(c, host_done);
+            return;
+        }
+        __syncthreads();
+    }
+    // 1. column sums of R = a K b at this batch end, before any absorption (R is invariant under it; a and
+    //    b are not): they go into the next snapshot
     if (final_dg && complete) {
-        const double *a = V.a[cur], *b = V.b[cur];
-        for (int i = threadIdx.x; i < I; i += kCheckThreads) V.r[i] = a[i] * V.s[i] * (double)J;
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) V.c[j] = b[j] * V.t[j] * (double)I;
+        const double *b = V.b[cur];
+        for (int j = threadIdx.x; j < J; j += kCheckThreads) V.cs[j] = b[j] * V.t[j] * (double)I;
     }
     // 2. stabilisation (:137-141, :211-216)
     if (stop & 1) {
@@ -515,51 +597,26 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         const double gb = sqrt(db) / (1.0 + sqrt(nb));
         gap = gb > ga ? gb : ga;  // Python max(ga, gb)
     } else {
-        // primal / dual from marginals only (SURVEY.md 8 a-note; optimal_transport.py:45-62):
-        //   eps R log R + R C = R (f_i + g_j)  =>  no I x J temporaries.
+        // final stage: snapshot this batch end (f and g are invariant under absorption, so taking them
+        // after step 2 is the same state); its gap is evaluated by the next check (step 0)
         const double *a = V.a[cur], *b = V.b[cur];
-        const double l1 = c->lambda1, l2 = c->lambda2, qm = c->q;
-        const double dx = 1.0 / (double)I, dy = 1.0 / (double)J;
-        double kl1 = 0.0, kl2 = 0.0, fr = 0.0, gc = 0.0, sr = 0.0, c1 = 0.0, c2 = 0.0;
         for (int i = threadIdx.x; i < I; i += kCheckThreads) {
-            const double r = V.r[i], p = V.p[i];
-            const double f = V.u[i] + eps * log(a[i]);
-            const double x = r * dy;
-            kl1 += dx * (x * log(x / p) - x + p);
-            fr += f * r;
-            sr += r;
-            c1 += (p * dx) * (exp(-f / l1) - 1.0);
+            V.fs[i] = V.u[i] + eps * log(a[i]);
+            V.as[i] = a[i];
         }
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) {
-            const double cj = V.c[j];
-            const double g = V.v[j] + eps * log(b[j]);
-            const double y = cj * dx;
-            kl2 += dy * (y * log(y / qm) - y + qm);
-            gc += g * cj;
-            c2 += (qm * dy) * (exp(-g / l2) - 1.0);
-        }
-        double k0 = 0.0;
-        for (int k = threadIdx.x; k < V.n_sumK0_part; k += kCheckThreads) k0 += V.sumK0_part[k];
-        kl1 = block_sum<kCheckThreads>(kl1, red);
-        kl2 = block_sum<kCheckThreads>(kl2, red);
-        fr = block_sum<kCheckThreads>(fr, red);
-        gc = block_sum<kCheckThreads>(gc, red);
-        sr = block_sum<kCheckThreads>(sr, red);
-        c1 = block_sum<kCheckThreads>(c1, red);
-        c2 = block_sum<kCheckThreads>(c2, red);
-        k0 = block_sum<kCheckThreads>(k0, red);
-        const double ij = (double)I * (double)J;
-        const double pri = l1 * kl1 + l2 * kl2 + (fr + gc - eps * sr + eps * k0) / ij;
-        const double dua = -l1 * c1 - l2 * c2 - eps * (sr - k0) / ij;
-        gap = (pri - dua) / fabs(pri);
+        for (int j = threadIdx.x; j < J; j += kCheckThreads) V.gs[j] = V.v[j] + eps * log(b[j]);
+        __syncthreads();
         if (threadIdx.x == 0) {
-            c->primal = pri;
-            c->dual = dua;
-            c->sumK0 = k0;
+            c->snap_valid = 1;
+            c->snap_iter = c->iter;
+            c->stop = 0;
+            c->batch_done = 0;
         }
+        publish(c, host_done);
+        return;
     }
-    const double threshold = final_dg ? c->tolerance : 1e-6;  // :127
-    const bool again = gap > threshold;                        // NaN leaves the while loop, :129
+    const double threshold = 1e-6;      // :127 (warm stages; the final stage is handled in step 0)
+    const bool again = gap > threshold;  // NaN leaves the while loop, :129
     __syncthreads();
     if (threadIdx.x == 0) {
         c->gap = gap;
@@ -571,11 +628,6 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         publish(c, host_done);
         return;
     }
-    if (final_dg) {
-        finish(V, c, cur, gap != gap ? WOTB_STATUS_NAN : WOTB_STATUS_CONVERGED);
-        publish(c, host_done);
-        return;
-    }
     // next epsilon stage: absorb at the old epsilon (:118-119), then shrink (:120)
     const double eps_next = c->eps_sched[stage + 1];
     absorb(V, c, cur, eps, eps_next);
@@ -584,6 +636,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         c->stage = stage + 1;
         set_eps(c, eps_next);
         c->need_build = 1;
+        c->snap_valid = 0;
         c->batch_iters = (stage + 1 == WOTB_N_STAGES - 1) ? c->batch_size : 5;  // :130
     }
     publish(c, host_done);
@@ -668,6 +721,7 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     const size_t o_a0 = take(off, dI), o_a1 = take(off, dI), o_b0 = take(off, dJ), o_b1 = take(off, dJ);
     const size_t o_eu = take(off, dI), o_ev = take(off, dJ), o_s = take(off, dI), o_t = take(off, dJ);
     const size_t o_lp = take(off, dI);
+    const size_t o_sf = take(off, dI), o_fs = take(off, dI), o_gs = take(off, dJ), o_cs = take(off, dJ), o_as = take(off, dI);
     const size_t o_r = take(off, dI), o_c = take(off, dJ);
     const size_t o_w = take(off, (size_t)ldw * 4), o_z = take(off, (size_t)I * 4);
     const size_t o_tc = take(off, (size_t)n_col_tiles * 4 + 64);
@@ -690,6 +744,12 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.lu = (double *)(base + o_eu);
     V.lv = (double *)(base + o_ev);
     V.lp = (double *)(base + o_lp);
+    V.sfirst = (double *)(base + o_sf);
+    V.fs = (double *)(base + o_fs);
+    V.gs = (double *)(base + o_gs);
+    V.cs = (double *)(base + o_cs);
+    V.as = (double *)(base + o_as);
+    V.rowsum = nullptr;
     V.s = (double *)(base + o_s);
     V.t = (double *)(base + o_t);
     V.r = (double *)(base + o_r);
@@ -890,6 +950,7 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
     const int build_grid = (int)(I < ctx->sm_count * 8 ? I : ctx->sm_count * 8);
     SolveVecs V;
     WOTB_TRY(carve_vectors(ctx, I, J, ld, n_row_blocks, n_col_tiles, build_grid, G, f, g, &V));
+    V.rowsum = rowsum;
     WOTB_TRY(ctx->ctrl.reserve(sizeof(SolveCtrl)));
     SolveCtrl *d_ctrl = ctx->ctrl.as<SolveCtrl>();
     WOTB_TRY(ctx->status.reserve(256));
@@ -924,17 +985,16 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
                 k_col<<<col_grid, kColThreads, 0, st>>>(K, ld, V, d_ctrl, rows_per_block);
             }
         }
-        if (h.solver == WOTB_SOLVER_DUALITY_GAP) k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 1, nullptr);
         launch_check(ctx, V, d_ctrl, host_done);
     };
-    const int per_seq = 2 + (plan.ok ? 1 : 2 * slots) + (h.solver == WOTB_SOLVER_DUALITY_GAP ? 1 : 0);
+    const int per_seq = 2 + (plan.ok ? 1 : 2 * slots);
     info->launches = 1;
     int rc = pump(ctx, prm->use_graph != 0, per_seq, plan.ok ? 1 : 2 * slots, sequence, info);
     if (rc != WOTB_OK) return rc;
 
     WOTB_CUDA(cudaMemcpyAsync(&h, d_ctrl, sizeof(h), cudaMemcpyDeviceToHost, st));
     WOTB_CUDA(cudaStreamSynchronize(st));
-    if (rowsum) {
+    if (rowsum && !h.rowsum_ready) {
         if (h.need_build) {  // an absorption was the last thing that happened: bring K up to date first
             SolveCtrl tmp = h;
             tmp.done = 0;

@@ -46,6 +46,10 @@ struct SolveCtrl {
     unsigned int grid_bar;  // arrival counter of the fused kernel's grid barrier (zeroed by k_build)
     unsigned long long seq;  // check kernels executed so far
     double eps_final, out_scale;
+    // ---- lazy duality-gap check (see k_check) --------------------------------------------------
+    int snap_valid;       // a final-stage state is waiting for its row sums
+    int rowsum_ready;     // V.rowsum holds the coupling row sums of the returned state
+    long long snap_iter;  // current_iter of the snapshot
     // ---- online kernel only --------------------------------------------------------------------
     double inv_median;  // 1 / np.median(raw squared distances), ot_model.py:252
     double c1, c2;      // log2(e)/eps and log2(e)/(eps*median): exponents are formed in base 2
@@ -61,6 +65,9 @@ struct SolveVecs {
     double *s, *t;    // K (b dy) and K^T (a dx) of the last matvecs
     double *r, *c;    // row / column sums of R = a K b at the last gap check
     double *f, *g;    // outputs
+    double *sfirst;   // K (b dy) of the first iteration of the current batch: the row sums of the snapshot
+    double *fs, *gs, *cs, *as;  // snapshot of the state at the last final-stage batch end (f, g, column sums, a)
+    double *rowsum;   // coupling row sums written by the device when it finishes from a snapshot (may be NULL)
     float *w, *z;     // fp32 copies of b*dy and a*dx fed to the matvecs (w padded to ld with zeros)
     double *colpart;  // [n_row_blocks, ldp] column partial sums
     unsigned int *tile_counters;

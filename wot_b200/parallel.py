@@ -151,7 +151,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         prm = _lib.make_params(solver=solver, kernel=_lib.KERNEL_ONLINE, **params)
         f = torch.empty(n_i, dtype=torch.float64, device=dev)
         g = torch.empty(n_j, dtype=torch.float64, device=dev)
-        exch = torch.zeros(max(n_i, n_j), dtype=torch.float64, device=dev)
+        exch = torch.zeros(max(2 * n_i, n_j), dtype=torch.float64, device=dev)
         solve = C.c_void_p()
         _lib.check(lib.wotb_online_open(h, P(X0), n_i, P(X1), n_j, d, median, P(Gd), C.byref(prm), rank, world, P(f),
                                         P(g), C.byref(solve)))
@@ -175,13 +175,10 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                 step(OP_BEGIN_B)
                 for _ in range(slots):
                     step(OP_ROW)
-                    reduce(n_i)
+                    reduce(2 * n_i)      # a-slices and their row sums (lazy duality-gap check)
                     step(OP_COL_PARTIAL)
                     reduce(n_j)
                     step(OP_COL_FINISH)
-                if solver == _lib.SOLVER_DUALITY_GAP:
-                    step(OP_GAP_ROWS)
-                    reduce(n_i)
                 step(OP_CHECK)
                 _lib.check(lib.wotb_online_state(solve, C.byref(info), C.byref(done)))
                 if done.value:
