@@ -200,6 +200,15 @@ void wotb_online_close(void *solve);
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
                           double *ms_fused /* one fused iteration (K read once), -1 if the shape is unsupported */);
 
+/* Kernel-level hook for tests and bench.py: one online-kernel pass (the K.(b dy) half of optimal_transport.py:133
+ * without materialising K),  sums[i] = sum_j exp2(off_out[i] + off_in[j] + scale^2 <x_out_i, x_in_j>),  all device
+ * pointers, float64.  impl 0: SIMT FP32 kernel, impl 1: tcgen05 (3xTF32 cross term + offsets in TMEM; d <= 38).
+ * ms_per_pass (may be NULL) = average device time of `reps` launches after one warm-up (CUDA events on the
+ * context's stream). */
+int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, const double *x_in, int64_t n_in, int32_t d,
+                            double scale, const double *off_out, const double *off_in, int32_t impl, int32_t reps,
+                            double *sums, double *ms_per_pass);
+
 /* Page-locked host memory for coupling outputs (cudaHostAlloc): a coupling written into it leaves the
  * device at PCIe speed; pageable destinations are served through an internal bounce buffer. */
 int wotb_pinned_alloc(size_t bytes, void **out);

@@ -82,6 +82,8 @@ void online_rows(OnlineSolve *, int64_t *, int64_t *);
 void online_close(OnlineSolve *);
 int sinkhorn_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const wotb_params *, double *, double *, double *, wotb_info *);
+int online_rowsums(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
+                   const double *, int, int, double *, double *);
 int coupling_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const double *, double, double, void *, int64_t, int, double *, cudaStream_t);
 
@@ -470,6 +472,12 @@ void wotb_online_close(void *solve) { online_close((OnlineSolve *)solve); }
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
                           double *ms_fused) {
     return bench_matvec(ctx, I, J, reps, ms_row, ms_col, ms_fused);
+}
+
+int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, const double *x_in, int64_t n_in, int32_t d,
+                            double scale, const double *off_out, const double *off_in, int32_t impl, int32_t reps,
+                            double *sums, double *ms_per_pass) {
+    return online_rowsums(ctx, x_out, n_out, x_in, n_in, d, scale, off_out, off_in, impl, reps, sums, ms_per_pass);
 }
 
 int wotb_pinned_alloc(size_t bytes, void **out) {

@@ -30,7 +30,7 @@ constexpr int kOnChunk = 32;     // coordinate dimensions per shared-memory chun
 struct OnlineSide {
     const float *T;   // k-major scaled coordinates: T[k * ld + index], ld % 128 == 0, zero padded
     long long ld;
-    const float *off; // exponent offsets of this side (padded with -inf)
+    const double *off; // exponent offsets of this side (padded with -inf); rounded to fp32 on load
     int n;            // valid entries
 };
 
@@ -63,6 +63,41 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// What a finished out entry does with its reduced sum s (shared by the SIMT and the tcgen05 pass kernels).
+// Returns |a| or |b| for the tau test of a half-step, 0 otherwise.
+template <bool COLPASS>
+__device__ __forceinline__ double online_apply(int mode, int o, double s, const SolveVecs &V, SolveCtrl *ctrl,
+                                               double *rowsum_out) {
+    const int I = ctrl->I, J = ctrl->J;
+    const int cur = ctrl->cur;
+    double vmax = 0.0;
+    if (mode == 0) {
+        if (!COLPASS) {
+            const double a = scaling_update(V.lp[o], s, ctrl->alpha1, V.lu[o]);
+            V.a[cur ^ 1][o] = a;
+            V.s[o] = s;
+            if (ctrl->batch_done == 0) V.sfirst[o] = s;
+            V.Pd[o] = (ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
+            vmax = fabs(a);
+        } else {
+            const double b = scaling_update(ctrl->lq, s, ctrl->alpha2, V.lv[o]);
+            V.b[cur ^ 1][o] = b;
+            V.t[o] = s;
+            V.Qd[o] = (ctrl->c1 * V.v[o] - ctrl->c2 * V.ny[o] + log2(b) - log2((double)J));
+            vmax = fabs(b);
+        }
+    } else if (mode == 1) {
+        V.s[o] = s;
+    } else if (mode == 2) {
+        rowsum_out[o] = V.a[cur][o] * s * (ctrl->out_scale * (double)J);
+    } else if (mode == 3) {
+        V.sumK0_part[o] = s;
+    } else {
+        rowsum_out[o] = s;
+    }
+    return vmax;
+}
+
 // mode 0: Sinkhorn half-step (row pass updates a, column pass updates b and closes the iteration)
 // mode 1: row sums only (duality-gap check)       mode 2: coupling row sums after the solve
 // mode 3: sum_ij exp(-C_ij/eps) row partials (final-stage `_K`, optimal_transport.py:121)
@@ -92,7 +127,7 @@ __global__ void __launch_bounds__(kOnThreads, 2)
 
     float poff[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) poff[r] = A.out.off[o0 + ty * 8 + r];
+    for (int r = 0; r < 8; ++r) poff[r] = (float)A.out.off[o0 + ty * 8 + r];
     double racc[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) racc[r] = 0.0;
@@ -161,10 +196,9 @@ __global__ void __launch_bounds__(kOnThreads, 2)
         if (chunk == n_chunks - 1) {
             // epilogue of this tile: exp2 and the row reduction
             float qoff[8];
-            const float4 qa = *reinterpret_cast<const float4 *>(A.in.off + (long long)tile * kOnTile + tx * 8);
-            const float4 qb = *reinterpret_cast<const float4 *>(A.in.off + (long long)tile * kOnTile + tx * 8 + 4);
-            qoff[0] = qa.x, qoff[1] = qa.y, qoff[2] = qa.z, qoff[3] = qa.w;
-            qoff[4] = qb.x, qoff[5] = qb.y, qoff[6] = qb.z, qoff[7] = qb.w;
+            const double *qsrc = A.in.off + (long long)tile * kOnTile + tx * 8;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) qoff[c] = (float)__ldg(qsrc + c);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 float sum = 0.f;
@@ -195,38 +229,13 @@ __global__ void __launch_bounds__(kOnThreads, 2)
     if (!is_last) return;
     __threadfence();
     // ---- last CTA of this out tile: sum the segments in order and apply the update ---------------
-    const int I = ctrl->I, J = ctrl->J;
-    const int cur = ctrl->cur;
     double vmax = 0.0;
     if (tid < kOnTile) {
         const int o = o0 + tid;
         if (o < A.out.n) {
             double s = 0.0;
             for (int sg = 0; sg < A.nseg; ++sg) s += __ldcg(A.part + (long long)sg * A.out.ld + o);
-            if (mode == 0) {
-                if (!COLPASS) {
-                    const double a = scaling_update(V.lp[o], s, ctrl->alpha1, V.lu[o]);
-                    V.a[cur ^ 1][o] = a;
-                    V.s[o] = s;
-                    if (ctrl->batch_done == 0) V.sfirst[o] = s;
-                    V.Pd[o] = (float)(ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
-                    vmax = fabs(a);
-                } else {
-                    const double b = scaling_update(ctrl->lq, s, ctrl->alpha2, V.lv[o]);
-                    V.b[cur ^ 1][o] = b;
-                    V.t[o] = s;
-                    V.Qd[o] = (float)(ctrl->c1 * V.v[o] - ctrl->c2 * V.ny[o] + log2(b) - log2((double)J));
-                    vmax = fabs(b);
-                }
-            } else if (mode == 1) {
-                V.s[o] = s;
-            } else if (mode == 2) {
-                rowsum_out[o] = V.a[cur][o] * s * (ctrl->out_scale * (double)J);
-            } else if (mode == 3) {
-                V.sumK0_part[o] = s;
-            } else {
-                rowsum_out[o] = s;
-            }
+            vmax = online_apply<COLPASS>(mode, o, s, V, ctrl, rowsum_out);
         }
     }
     if (mode == 0) {
@@ -264,13 +273,13 @@ __global__ void k_online_scale(const double *__restrict__ x, int n, int d, float
 }
 
 // S0 offsets (-c2 |x|^2) for the final stage and the need_build handshake.
-__global__ void k_online_s0_offsets(SolveVecs V, SolveCtrl *ctrl, float *p0, float *q0) {
+__global__ void k_online_s0_offsets(SolveVecs V, SolveCtrl *ctrl, double *p0, double *q0) {
     if (ctrl->done || !ctrl->need_build) return;
     const int I = ctrl->I, J = ctrl->J;
     const double c2 = ctrl->c2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < V.n_pad_i) p0[idx] = idx < I ? (float)(-c2 * V.nx[idx]) : -INFINITY;
-    if (idx < V.n_pad_j) q0[idx] = idx < J ? (float)(-c2 * V.ny[idx]) : -INFINITY;
+    if (idx < V.n_pad_i) p0[idx] = idx < I ? (-c2 * V.nx[idx]) : -INFINITY;
+    if (idx < V.n_pad_j) q0[idx] = idx < J ? (-c2 * V.ny[idx]) : -INFINITY;
 }
 
 __global__ void k_online_built(SolveCtrl *ctrl) {
@@ -321,16 +330,16 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
     };
     const size_t o_xt = take((size_t)dp * ldi * 4), o_yt = take((size_t)dp * ldj * 4);
     const size_t o_nx = take((size_t)I * 8), o_ny = take((size_t)J * 8);
-    const size_t o_ps = take((size_t)ldi * 4), o_qs = take((size_t)ldj * 4);
-    const size_t o_pd = take((size_t)ldi * 4), o_qd = take((size_t)ldj * 4);
-    const size_t o_p0 = take((size_t)ldi * 4), o_q0 = take((size_t)ldj * 4);
+    const size_t o_ps = take((size_t)ldi * 8), o_qs = take((size_t)ldj * 8);
+    const size_t o_pd = take((size_t)ldi * 8), o_qd = take((size_t)ldj * 8);
+    const size_t o_p0 = take((size_t)ldi * 8), o_q0 = take((size_t)ldj * 8);
     const size_t o_part = take((size_t)(nseg_row > nseg_col ? nseg_row : nseg_col) * (ldi > ldj ? ldi : ldj) * 8);
     const size_t o_cnt = take((size_t)(tiles_i + tiles_j) * 4 + 64);
     WOTB_TRY(ctx->onl.reserve(off));
     char *ob = ctx->onl.as<char>();
     float *XT = (float *)(ob + o_xt), *YT = (float *)(ob + o_yt);
     double *nx = (double *)(ob + o_nx), *ny = (double *)(ob + o_ny);
-    float *P0 = (float *)(ob + o_p0), *Q0 = (float *)(ob + o_q0);
+    double *P0 = (double *)(ob + o_p0), *Q0 = (double *)(ob + o_q0);
     double *part = (double *)(ob + o_part);
     unsigned int *cnt_i = (unsigned int *)(ob + o_cnt), *cnt_j = cnt_i + tiles_i;
     WOTB_CUDA(cudaMemsetAsync(cnt_i, 0, (size_t)(tiles_i + tiles_j) * 4, st));
@@ -340,10 +349,10 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
     V.online = 1;
     V.nx = nx;
     V.ny = ny;
-    V.Ps = (float *)(ob + o_ps);
-    V.Qs = (float *)(ob + o_qs);
-    V.Pd = (float *)(ob + o_pd);
-    V.Qd = (float *)(ob + o_qd);
+    V.Ps = (double *)(ob + o_ps);
+    V.Qs = (double *)(ob + o_qs);
+    V.Pd = (double *)(ob + o_pd);
+    V.Qd = (double *)(ob + o_qd);
     V.n_pad_i = ldi;
     V.n_pad_j = ldj;
     V.rowsum = rowsum;
@@ -459,7 +468,7 @@ __global__ void k_import_a(SolveVecs V, SolveCtrl *ctrl, const double *__restric
         const double a = src[i];
         V.a[ctrl->cur ^ 1][i] = a;
         if (ctrl->batch_done == 0) V.sfirst[i] = src[I + i];
-        V.Pd[i] = (float)(ctrl->c1 * V.u[i] - ctrl->c2 * V.nx[i] + log2(a) - log2((double)I));
+        V.Pd[i] = (ctrl->c1 * V.u[i] - ctrl->c2 * V.nx[i] + log2(a) - log2((double)I));
         vmax = fabs(a);
     }
     vmax = warp_max(vmax);
@@ -486,7 +495,7 @@ __global__ void k_online_col_finish(SolveVecs V, SolveCtrl *ctrl, const double *
         const double b = scaling_update(ctrl->lq, t, ctrl->alpha2, V.lv[j]);
         V.b[cur ^ 1][j] = b;
         V.t[j] = t;
-        V.Qd[j] = (float)(ctrl->c1 * V.v[j] - ctrl->c2 * V.ny[j] + log2(b) - log2((double)J));
+        V.Qd[j] = (ctrl->c1 * V.v[j] - ctrl->c2 * V.ny[j] + log2(b) - log2((double)J));
         vmax = fabs(b);
     }
     vmax = warp_max(vmax);
@@ -509,7 +518,8 @@ struct OnlineSolve {
     int d, dp;
     int64_t ldi, ldj;
     const double *x0, *x1;
-    float *XT, *YT, *P0, *Q0;
+    float *XT, *YT;
+    double *P0, *Q0;
     SolveVecs V;
     SolveCtrl *d_ctrl;
     SolveCtrl h;
@@ -564,16 +574,16 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     };
     const size_t o_xt = take((size_t)dp * ldi * 4), o_yt = take((size_t)dp * ldj * 4);
     const size_t o_nx = take((size_t)I * 8), o_ny = take((size_t)J * 8);
-    const size_t o_ps = take((size_t)ldi * 4), o_qs = take((size_t)ldj * 4);
-    const size_t o_pd = take((size_t)ldi * 4), o_qd = take((size_t)ldj * 4);
-    const size_t o_p0 = take((size_t)ldi * 4), o_q0 = take((size_t)ldj * 4);
+    const size_t o_ps = take((size_t)ldi * 8), o_qs = take((size_t)ldj * 8);
+    const size_t o_pd = take((size_t)ldi * 8), o_qd = take((size_t)ldj * 8);
+    const size_t o_p0 = take((size_t)ldi * 8), o_q0 = take((size_t)ldj * 8);
     const size_t o_part = take((size_t)(nseg_row > nseg_col ? nseg_row : nseg_col) * (ldi > ldj ? ldi : ldj) * 8);
     const size_t o_cnt = take((size_t)(tiles_i + tiles_j) * 4 + 64);
     WOTB_TRY(ctx->onl.reserve(off));
     char *ob = ctx->onl.as<char>();
     S->XT = (float *)(ob + o_xt), S->YT = (float *)(ob + o_yt);
     double *nx = (double *)(ob + o_nx), *ny = (double *)(ob + o_ny);
-    S->P0 = (float *)(ob + o_p0), S->Q0 = (float *)(ob + o_q0);
+    S->P0 = (double *)(ob + o_p0), S->Q0 = (double *)(ob + o_q0);
     double *part = (double *)(ob + o_part);
     unsigned int *cnt_i = (unsigned int *)(ob + o_cnt), *cnt_j = cnt_i + tiles_i;
     WOTB_CUDA(cudaMemsetAsync(cnt_i, 0, (size_t)(tiles_i + tiles_j) * 4, st));
@@ -581,8 +591,8 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     SolveVecs &V = S->V;
     V.online = 1;
     V.nx = nx, V.ny = ny;
-    V.Ps = (float *)(ob + o_ps), V.Qs = (float *)(ob + o_qs);
-    V.Pd = (float *)(ob + o_pd), V.Qd = (float *)(ob + o_qd);
+    V.Ps = (double *)(ob + o_ps), V.Qs = (double *)(ob + o_qs);
+    V.Pd = (double *)(ob + o_pd), V.Qd = (double *)(ob + o_qd);
     V.n_pad_i = ldi, V.n_pad_j = ldj;
     V.rowsum = V.r;  // row sums of a snapshot finish land here (V.r is free once the solve is done)
     WOTB_TRY(ctx->ctrl.reserve(sizeof(SolveCtrl)));

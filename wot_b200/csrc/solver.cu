@@ -354,8 +354,8 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
         V.lu[i] = -u * i1;
         if (V.online) {
             const double ps = c1 * u - c2 * V.nx[i];
-            V.Ps[i] = (float)ps;
-            V.Pd[i] = (float)(ps + l2dx);
+            V.Ps[i] = ps;
+            V.Pd[i] = (ps + l2dx);
         } else {
             V.z[i] = dxf;
         }
@@ -367,8 +367,8 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
         V.lv[j] = -v * i2;
         if (V.online) {
             const double qs = c1 * v - c2 * V.ny[j];
-            V.Qs[j] = (float)qs;
-            V.Qd[j] = (float)(qs + l2dy);
+            V.Qs[j] = qs;
+            V.Qd[j] = (qs + l2dy);
         } else {
             V.w[j] = dyf;
         }
@@ -658,8 +658,8 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
         V.s[i] = 0.0;
         if (V.online) {
             const double ps = -ctrl->c2 * V.nx[i];
-            V.Ps[i] = (float)ps;
-            V.Pd[i] = (float)(ps - log2((double)I));
+            V.Ps[i] = ps;
+            V.Pd[i] = (ps - log2((double)I));
         } else {
             V.z[i] = dxf;
         }
@@ -674,8 +674,8 @@ __global__ void __launch_bounds__(kCheckThreads) k_init(SolveVecs V, SolveCtrl *
                 V.b[1][j] = 1.0;
                 V.lv[j] = 0.0;
                 V.t[j] = 0.0;
-                V.Qs[j] = (float)qs;
-                V.Qd[j] = (float)(qs - log2((double)J));
+                V.Qs[j] = qs;
+                V.Qd[j] = (qs - log2((double)J));
             } else {
                 V.Qs[j] = V.Qd[j] = -INFINITY;
             }
@@ -1106,6 +1106,7 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
 }  // namespace wotb
 
 #include "online_pass.cuh"
+#include "online_tc.cuh"
 
 namespace wotb {
 int sinkhorn_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,

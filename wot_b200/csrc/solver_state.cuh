@@ -77,7 +77,7 @@ struct SolveVecs {
     // ---- online kernel only: exponent offsets, log2 domain (see online.cu) ----------------------
     int online;
     const double *nx, *ny;  // raw squared norms of the coordinates
-    float *Ps, *Qs;         // c1 u_i - c2 |x_i|^2 and c1 v_j - c2 |y_j|^2   (change on absorption / new eps)
-    float *Pd, *Qd;         // Ps + log2(a_i / I) and Qs + log2(b_j / J)      (change every half-step)
+    double *Ps, *Qs;         // c1 u_i - c2 |x_i|^2 and c1 v_j - c2 |y_j|^2   (change on absorption / new eps)
+    double *Pd, *Qd;         // Ps + log2(a_i / I) and Qs + log2(b_j / J)      (change every half-step)
     long long n_pad_i, n_pad_j;  // padded lengths; padding holds -inf so padded entries add exp2(-inf) = 0
 };
