@@ -209,6 +209,10 @@ int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, c
                             double scale, const double *off_out, const double *off_in, int32_t impl, int32_t reps,
                             double *sums, double *ms_per_pass);
 
+/* Measured MUFU.EX2 throughput of the device (ex2 per second, all SMs): the roofline denominator of the online
+ * kernels. */
+int wotb_bench_mufu_dev(wotb_ctx *ctx, double *ex2_per_s);
+
 /* Page-locked host memory for coupling outputs (cudaHostAlloc): a coupling written into it leaves the
  * device at PCIe speed; pageable destinations are served through an internal bounce buffer. */
 int wotb_pinned_alloc(size_t bytes, void **out);

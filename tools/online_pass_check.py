@@ -60,6 +60,11 @@ def main():
     ctx = _lib.context(0)
     impls = [int(v) for v in args.impls.split(",")]
     names = {0: "simt", 1: "tcgen05"}
+    for dbg in range(1, 16):
+        names[1 + 16 * dbg] = "tcgen05" + "".join(t for b, t in ((1, " no-mma"), (2, " no-exp"), (8, " prof")) if dbg & b)
+    peak = C.c_double()
+    _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak)))
+    print("MUFU.EX2 peak (measured): %.3f T ex2/s" % (peak.value / 1e12), flush=True)
     for shape in args.check:
         n_out, n_in = (int(v) for v in shape.split("x"))
         x0, x1, scale, po, pi = make_inputs(n_out, n_in, args.d, seed=5)
@@ -67,7 +72,7 @@ def main():
         for impl in impls:
             got, ms = run(ctx, torch, x0, x1, scale, po, pi, impl, 1)
             err = np.abs(got - want) / want
-            print("check %6d x %6d d=%d %-8s max rel err %.3e  mean %.3e  (sum range %.3g..%.3g)"
+            print("check %6d x %6d d=%d %-14s max rel err %.3e  mean %.3e  (sum range %.3g..%.3g)"
                   % (n_out, n_in, args.d, names[impl], err.max(), err.mean(), want.min(), want.max()), flush=True)
     for shape in args.time:
         n_out, n_in = (int(v) for v in shape.split("x"))
@@ -75,8 +80,8 @@ def main():
         for impl in impls:
             _, ms = run(ctx, torch, x0, x1, scale, po, pi, impl, 20)
             ent = n_out * n_in
-            print("time  %6d x %6d d=%d %-8s %.1f us/pass  %.2f T entries/s" % (n_out, n_in, args.d, names[impl],
-                                                                                ms * 1e3, ent / ms / 1e9), flush=True)
+            print("time  %6d x %6d d=%d %-22s %.1f us/pass  %.2f T entries/s  %.3f of MUFU peak"
+                  % (n_out, n_in, args.d, names[impl], ms * 1e3, ent / ms / 1e9, ent / ms * 1e3 / peak.value), flush=True)
 
 
 if __name__ == "__main__":

@@ -76,6 +76,7 @@ SIGNATURES = {
     "wotb_online_close": (None, [_P]),
     "wotb_bench_matvec_dev": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "wotb_online_rowsums_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _P, _P, _I32, _I32, _P, C.POINTER(_D)]),
+    "wotb_bench_mufu_dev": (C.c_int, [_P, C.POINTER(_D)]),
     "wotb_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "wotb_pinned_free": (None, [_P]),
 }

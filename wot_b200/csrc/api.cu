@@ -84,6 +84,7 @@ int sinkhorn_online(wotb_ctx *, const double *, int64_t, const double *, int64_t
                     const wotb_params *, double *, double *, double *, wotb_info *);
 int online_rowsums(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                    const double *, int, int, double *, double *);
+int bench_mufu(wotb_ctx *, double *);
 int coupling_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const double *, double, double, void *, int64_t, int, double *, cudaStream_t);
 
@@ -479,6 +480,8 @@ int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, c
                             double *sums, double *ms_per_pass) {
     return online_rowsums(ctx, x_out, n_out, x_in, n_in, d, scale, off_out, off_in, impl, reps, sums, ms_per_pass);
 }
+
+int wotb_bench_mufu_dev(wotb_ctx *ctx, double *ex2_per_s) { return bench_mufu(ctx, ex2_per_s); }
 
 int wotb_pinned_alloc(size_t bytes, void **out) {
     WOTB_REQUIRE(out != nullptr, "out is NULL");

@@ -3,32 +3,38 @@
 // The half-step of optimal_transport.py:133-134 in the online form (see online_pass.cuh) is
 //     s_i = sum_j exp2( P_i + Q_j + <X_i, Y_j> )
 // with X, Y the coordinates scaled by sqrt(2 log2(e) / (eps median)).  The SIMT kernel spends d FFMA per
-// entry on the cross term, which makes it FP32-bound at 1/3 of what the MUFU pipe could do.  Here the
-// WHOLE exponent comes out of the tensor cores: every point is a row of 2*kseg fp32 values
-//     [ hi(x_0..x_{d-1}), 0.., s_A, s_B | lo(x_0..x_{d-1}), 0.., s_A', s_B' ]        kseg = round_up(d + 2, 8)
-// where hi/lo is the 2-term TF32 split (x = hi + lo, both exactly representable in TF32) and the two spare
-// K slots carry the offsets:  "out" rows (A operand) hold (1, a1 | 0, a2), "in" rows (B operand) hold
-// (b1, 1 | b2, 0) with P_i = a1 + a2 + resid_i and Q_j = b1 + b2 (TF32 pairs, 22 bits).  Three K segments
-// (A_hi.B_hi + A_lo.B_hi + A_hi.B_lo, the 3xTF32 scheme; the dropped lo.lo term is 2^-22 relative) give
-//     D_ij = <X_i, Y_j> + a1 + a2 + b1 + b2
-// in the fp32 TMEM accumulator, so the epilogue is ONE MUFU.EX2 and one FADD per entry; resid_i (the part
-// of P_i below 22 bits) multiplies the finished row sum in float64.  Tolerance gate (BASELINE.json
-// north_star: tensor cores only for the cross term "if the stated tolerance holds"): the exponent error
-// is ~1e-5 absolute at eps = 0.05, the same as the fp32 SIMT kernel; tests/test_gpu_parity.py holds both
-// to the 1e-4 coupling criterion.
+// entry on the cross term, which makes it FP32-bound at 1/5 of what the MUFU pipe could do.  Here the
+// WHOLE exponent comes out of the tensor cores.  Every point is a row of 3*kseg fp16 values,
+// kseg = round_up(d + 2, 16), built from the 2-term split x = hi + 2^-11 lo' (hi = fp16(x),
+// lo' = fp16((x - hi) 2^11): 22 bits, products exact in the fp32 accumulator):
+//     A role ("out" rows):  [ hi | lo' | hs ]      B role ("in" rows):  [ hi | hs | lo' ]      hs = 2^-11 hi
+// so one plain K = 3*kseg GEMM gives hi.hi + 2^-11 (lo'.hi + hi.lo'); the dropped lo.lo term is 2^-22
+// relative.  (Measured on B200: a tcgen05.mma costs ~64 + N/2 clocks whatever the operand type, so the fp16
+// K = 16 instruction does the work of two TF32 K = 8 ones; with 3xTF32 the pass was tensor-bound at 0.48 of
+// the MUFU peak.)  The two spare K slots of every segment carry the offsets: A rows hold (1, a1 | 0, a2' |
+// 2^-11, 0), B rows hold (b1, 1 | 0, 2^-11 | b2', 0), P_i = a1 + 2^-11 a2' + resid_i, Q_j = b1 + 2^-11 b2',
+// so
+//     D_ij = <X_i, Y_j> + P_i - resid_i + Q_j
+// lands in the fp32 TMEM accumulator and the epilogue is ONE MUFU.EX2 and one FADD per entry; resid_i (the
+// part of P_i below 22 bits) multiplies the finished row sum in float64.  Tolerance gate (BASELINE.json
+// north_star: tensor cores only for the cross term "if the stated tolerance holds"): the exponent error is
+// ~1e-5 absolute at eps = 0.05, the same as the fp32 SIMT kernel; tests/test_gpu_parity.py holds both to
+// the 1e-4 coupling criterion.
 //
 // CTA = 256 out rows (two 128-row A blocks resident in shared memory) x one segment of the in side, which
 // streams through a ring of 128-row B tiles: one cp.async.bulk per tile, because the operand arrays are
 // kept in HBM in exactly the canonical K-major no-swizzle UMMA layout (8-row groups of 16-byte chunks), so
-// a tile is a contiguous 32 KB block.  Per B tile the MMA thread issues 2 x 3 x kseg/8 tcgen05.mma
-// (M = 128, N = 128, K = 8) into two of four 128-column TMEM accumulators; eight epilogue warps (one
-// warpgroup per row block, thread = row) drain them with tcgen05.ld, exp2 and an in-thread sum: no
-// shuffles, no shared memory.  L2 traffic is 1 byte per entry; nothing of size I x J exists anywhere.
+// a tile is a contiguous 24 KB block.  Per B tile the MMA thread issues 2 x 3*kseg/16 tcgen05.mma
+// (kind::f16, M = 128, N = 128, K = 16) into two of four 128-column TMEM accumulators; eight epilogue
+// warps (one warpgroup per row block, thread = row) drain them with tcgen05.ld, exp2 and an in-thread sum:
+// no shuffles, no shared memory.  L2 traffic is 0.75 byte per entry; nothing of size I x J exists anywhere.
 //
 // Warp roles (384 threads): warp 0 lane 0 TMA producer, warp 1 TMEM allocation + MMA issue (lane 0),
 // warps 4..11 epilogue.  Pipelines: full/empty per B stage (TMA <-> MMA), acc_full/acc_empty per TMEM
 // buffer (MMA <-> epilogue).
 #pragma once
+
+#include <cuda_fp16.h>
 
 #include "online_pass.cuh"
 
@@ -36,87 +42,97 @@ namespace wotb {
 
 constexpr int kTcM = 128;                 // rows per accumulator (UMMA M)
 constexpr int kTcRowBlocks = 2;           // A blocks per CTA
-constexpr int kTcOut = kTcM * kTcRowBlocks;
+constexpr int kTcOut = kTcM * kTcRowBlocks;  // row padding of every operand array
 constexpr int kTcN = 128;                 // in-side rows per B tile (UMMA N)
-constexpr int kTcMaxStages = 4;
+constexpr int kTcAccCols = kTcRowBlocks * kTcN;  // TMEM columns per accumulator buffer (two buffers = all 512)
+constexpr int kTcTail = 2048;             // barriers + reduction scratch after the operand stages
+constexpr int kTcMaxStages = 6;
 constexpr int kTcThreads = 384;
 constexpr int kTcEpiWarp0 = 4;            // first epilogue warp (multiple of 4: warp % 4 selects the TMEM lane quadrant)
-constexpr int kTcMaxKseg = 40;            // d <= 38
+constexpr int kTcMaxKseg = 48;            // d <= 46
 constexpr int kTcTmemCols = 512;
-constexpr float kTcPad = -65536.f;        // offset of padded in rows: exp2 underflows to exactly 0
+constexpr float kTcPad = -60000.f;        // offset of padded in rows (finite in fp16): exp2 underflows to exactly 0
 constexpr int kTcSmemLimit = 232448;
 
-// element k (0 <= k < 2*kseg: hi segment then lo segment) of row r; kc = 16-byte chunks per row = kseg / 2
+// half-precision element k (0 <= k < 3*kseg: the three segments) of row r; kc = 16-byte chunks per row = 3*kseg/8
 __host__ __device__ __forceinline__ long long tc_index(long long r, int k, int kc) {
-    return ((r >> 3) * kc + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
+    return ((r >> 3) * kc + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
 }
 
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t y;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(y) : "f"(x));
-    return __uint_as_float(y);
+constexpr float kTcLoScale = 2048.f;              // 2^11
+constexpr float kTcLoInv = 1.f / 2048.f;
+
+// x = hi + 2^-11 lo' with hi, lo' in fp16 (round to nearest).  |x| must stay below the fp16 range (6.5e4).
+__device__ __forceinline__ void tc_split(double x, __half &hi, __half &lo) {
+    hi = __double2half(x);
+    lo = __double2half((x - (double)__half2float(hi)) * 2048.0);
 }
 
 // ---- operand preparation ------------------------------------------------------------------------
-// Coordinates (scaled for the current epsilon, optionally centred) into both operand roles of one side.
+// Coordinates (scaled for the current epsilon) into both operand roles of one side.
 // The online analogue of rebuilding K (optimal_transport.py:124,:140): runs when need_build is set.
 __global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long rows_pad, int kseg,
-                          float *__restrict__ opA, float *__restrict__ opB, const SolveCtrl *ctrl, double scale) {
+                          __half *__restrict__ opA, __half *__restrict__ opB, const SolveCtrl *ctrl, double scale) {
     if (ctrl && (ctrl->done || !ctrl->need_build)) return;
     const double sc = ctrl ? sqrt(2.0 * ctrl->c2) : scale;
-    const int cpr = kseg >> 2;  // 16-byte chunks per segment
+    const int cps = kseg >> 3;  // 16-byte chunks per segment
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows_pad * cpr) return;
+    if (idx >= rows_pad * cps) return;
     const int r_lo = (int)(idx & 7);
-    const int c = (int)((idx >> 3) % cpr);
-    const long long r = (idx / (8 * cpr)) * 8 + r_lo;
-    float ha[4], la[4], hb[4], lb[4];
+    const int c = (int)((idx >> 3) % cps);
+    const long long r = (idx / (8 * cps)) * 8 + r_lo;
+    __align__(16) __half hi[8], lo[8], hs[8];
+    __align__(16) __half bhi[8], blo[8], bhs[8];
+    const __half zero = __float2half(0.f), one = __float2half(1.f), tiny = __float2half(kTcLoInv);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int k = 4 * c + e;
+    for (int e = 0; e < 8; ++e) {
+        const int k = 8 * c + e;
         double val = 0.0;
         if (r < n && k < d) val = sc * x[r * d + k];
-        const float h = tf32_rn((float)val);
-        const float l = tf32_rn((float)(val - (double)h));
-        ha[e] = hb[e] = h;
-        la[e] = lb[e] = l;
-        if (k == kseg - 2) {  // A: the 1 that picks up b1, b2;  B: b1 (set by k_tc_slots; padding rows stay at kTcPad)
-            ha[e] = 1.f, la[e] = 0.f;
-            hb[e] = r < n ? 0.f : kTcPad, lb[e] = 0.f;
-        } else if (k == kseg - 1) {  // A: a1, a2 (set by k_tc_slots);  B: the 1 that picks up a1, a2
-            ha[e] = 0.f, la[e] = 0.f;
-            hb[e] = 1.f, lb[e] = 0.f;
+        tc_split(val, hi[e], lo[e]);
+        hs[e] = __float2half(__half2float(hi[e]) * kTcLoInv);
+        bhi[e] = hi[e], blo[e] = lo[e], bhs[e] = hs[e];
+        if (k == kseg - 2) {
+            // A: (1 | 0 | 2^-11) picks up b1 and b2';  B: (b1 | 0 | b2') set by k_tc_slots, padding rows stay at kTcPad
+            hi[e] = one, lo[e] = zero, hs[e] = tiny;
+            bhi[e] = r < n ? zero : __float2half(kTcPad), bhs[e] = zero, blo[e] = zero;
+        } else if (k == kseg - 1) {
+            // A: (a1 | a2' | 0) set by k_tc_slots;  B: (1 | 2^-11 | 0) picks up a1 and a2'
+            hi[e] = zero, lo[e] = zero, hs[e] = zero;
+            bhi[e] = one, bhs[e] = tiny, blo[e] = zero;
         }
     }
-    const int kc = kseg >> 1;
-    *reinterpret_cast<float4 *>(opA + tc_index(r, 4 * c, kc)) = make_float4(ha[0], ha[1], ha[2], ha[3]);
-    *reinterpret_cast<float4 *>(opA + tc_index(r, kseg + 4 * c, kc)) = make_float4(la[0], la[1], la[2], la[3]);
-    *reinterpret_cast<float4 *>(opB + tc_index(r, 4 * c, kc)) = make_float4(hb[0], hb[1], hb[2], hb[3]);
-    *reinterpret_cast<float4 *>(opB + tc_index(r, kseg + 4 * c, kc)) = make_float4(lb[0], lb[1], lb[2], lb[3]);
+    const int kc = 3 * cps;
+    *reinterpret_cast<uint4 *>(opA + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hi);
+    *reinterpret_cast<uint4 *>(opA + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(lo);
+    *reinterpret_cast<uint4 *>(opA + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hs);
+    *reinterpret_cast<uint4 *>(opB + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhi);
+    *reinterpret_cast<uint4 *>(opB + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhs);
+    *reinterpret_cast<uint4 *>(opB + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(blo);
 }
 
 // Exponent offsets into the spare K slots: the out side's static offsets into its A-role rows (+ the
 // float64 residual), the in side's current offsets into its B-role rows.  Runs before every pass.
-__global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, float *__restrict__ opA_out,
+__global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half *__restrict__ opA_out,
                            double *__restrict__ resid, const double *__restrict__ off_in, int n_in,
-                           float *__restrict__ opB_in, int kseg, const SolveCtrl *ctrl) {
+                           __half *__restrict__ opB_in, int kseg, const SolveCtrl *ctrl) {
     if (ctrl && ctrl->done) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int kc = kseg >> 1;
+    const int kc = 3 * (kseg >> 3);
     if (i < n_out) {
-        const double al = fmax(off_out[i], -60000.0);
-        const float a1 = tf32_rn((float)al);
-        const float a2 = tf32_rn((float)(al - (double)a1));
-        resid[i] = al - (double)a1 - (double)a2;
+        const double al = fmax(off_out[i], (double)kTcPad);
+        __half a1, a2;
+        tc_split(al, a1, a2);
+        resid[i] = al - (double)__half2float(a1) - (double)__half2float(a2) * (double)kTcLoInv;
         opA_out[tc_index(i, kseg - 1, kc)] = a1;
         opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
     }
     if (i < n_in) {
-        const double be = fmax(off_in[i], -60000.0);
-        const float b1 = tf32_rn((float)be);
-        const float b2 = tf32_rn((float)(be - (double)b1));
+        const double be = fmax(off_in[i], (double)kTcPad);
+        __half b1, b2;
+        tc_split(be, b1, b2);
         opB_in[tc_index(i, kseg - 2, kc)] = b1;
-        opB_in[tc_index(i, 2 * kseg - 2, kc)] = b2;
+        opB_in[tc_index(i, 3 * kseg - 2, kc)] = b2;
     }
 }
 
@@ -148,10 +164,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
     return desc;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
+// warp-uniform wait: lane 0 polls, the warp reconverges behind it
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    mbar_wait_bounded(bar, parity);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
-        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(
             tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -196,25 +224,27 @@ __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
 }
 
 struct TcArgs {
-    const float *opA;     // out side, A role (UMMA layout, rows padded to kTcOut)
-    const float *opB;     // in side, B role (rows padded to kTcOut)
+    const __half *opA;    // out side, A role (UMMA layout, rows padded to kTcOut)
+    const __half *opB;    // in side, B role (rows padded to kTcOut)
     const double *resid;  // out side: float64 residual of the static offsets
     int out_n;            // valid out entries
     long long out_ld;     // stride of the partial-sum rows (>= padded out rows)
-    int kseg;             // K elements per TF32 segment (multiple of 8, >= d + 2)
+    int kseg;             // K elements per segment (multiple of 16, >= d + 2)
     int n_stages;         // B ring depth
     int nseg;             // segments of the in side (grid.y)
     int seg_tiles;        // B tiles per segment
     double *part;         // [nseg][out_ld] partial sums
     unsigned int *counters;  // one per out block
-    int out_blk0;         // first out block (256 rows) of this launch
-    int in_tile0;         // first in tile (128 rows) that is reduced over
+    int out_blk0;         // first out block (RB * 128 rows) of this launch
+    int in_tile0;         // first in tile (NT rows) that is reduced over
     int in_ntiles;        // number of in tiles reduced over
+    int dbg;              // measurement only: bit0 skip the MMAs, bit1 skip the exp2 work, bit3 write cycle counters
+    long long *prof;      // [CTA][8 epilogue warps][4]: cycles total, waiting for accumulators, waiting for tcgen05.ld, tiles
 };
 
 // modes as in k_online_pass: 0 half-step, 1 row sums for the gap, 2 coupling row sums, 3 S0 partials,
 // 4 partial sums only (row-sharded solves)
-template <bool COLPASS>
+template <bool COLPASS, int KSEG>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_online_tc(TcArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
     if (mode == 0 || mode == 4) {
@@ -226,20 +256,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             ctrl->stage != WOTB_N_STAGES - 1)
             return;
     }
+    constexpr int RB = kTcRowBlocks, NT = kTcN;
     extern __shared__ __align__(128) unsigned char tc_smem[];
     __shared__ int is_last;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int kseg = A.kseg;
-    const uint32_t row_bytes = (uint32_t)kseg * 8u;  // 2 * kseg floats
-    const uint32_t a_bytes = kTcM * row_bytes, b_bytes = kTcN * row_bytes;
+    constexpr int kseg = KSEG;
+    constexpr uint32_t row_bytes = (uint32_t)kseg * 6u;  // 3 * kseg halves
+    constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
     const int S = A.n_stages;
     unsigned char *sA = tc_smem;
-    unsigned char *sB = sA + kTcRowBlocks * a_bytes;
+    unsigned char *sB = sA + RB * a_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)S * b_bytes);
     uint64_t *empty = full + kTcMaxStages;
-    uint64_t *acc_full = empty + kTcMaxStages;
-    uint64_t *acc_empty = acc_full + 2;
-    uint64_t *a_full = acc_empty + 2;
+    uint64_t *acc_full = empty + kTcMaxStages;  // [buffer][row block]
+    uint64_t *acc_empty = acc_full + 2 * RB;
+    uint64_t *a_full = acc_empty + 2 * RB;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
 
     const int out_blk = blockIdx.x + A.out_blk0;
@@ -253,9 +284,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 2 * RB; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 8);
+            mbar_init(&acc_empty[b], 4);  // the four warps of the warpgroup that drains it
         }
         mbar_init(a_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -276,9 +307,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (wid == 0) {
         if (lane == 0 && n_tiles > 0) {
             // ===== TMA producer: the two A blocks once, then the B ring =====
-            mbar_expect_tx(a_full, kTcRowBlocks * a_bytes);
+            mbar_expect_tx(a_full, RB * a_bytes);
             const unsigned char *srcA = reinterpret_cast<const unsigned char *>(A.opA) + (size_t)o0 * row_bytes;
-            for (int rb = 0; rb < kTcRowBlocks; ++rb)
+            for (int rb = 0; rb < RB; ++rb)
                 bulk_g2s(sA + rb * a_bytes, srcA + (size_t)rb * a_bytes, a_bytes, a_full);
             const unsigned char *srcB = reinterpret_cast<const unsigned char *>(A.opB);
             for (int t = 0; t < n_tiles; ++t) {
@@ -289,74 +320,125 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
         }
     } else if (wid == 1) {
-        if (lane == 0 && n_tiles > 0) {
-            // ===== MMA issuer =====
-            // instruction descriptor: D fp32, A/B TF32, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
-                                   ((uint32_t)(kTcM >> 4) << 24);
-            const uint32_t lbo = 128u, sbo = (uint32_t)kseg * 64u;  // 16-byte chunks per row = kseg/2, 128 B each
-            const uint32_t lo_off = (uint32_t)(kseg >> 2) * 128u;   // byte offset of the lo segment inside an 8-row group
-            const int ksteps = kseg >> 3;
+        if (n_tiles > 0) {
+            // ===== MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected
+            // lane issues.  Issue-side cost matters: with per-lane descriptor arithmetic the issuing thread, not
+            // the tensor pipe, bounded the pass (~100 clocks per instruction, measured) =====
+            // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N, M
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+            const bool skip_mma = (A.dbg & 1) != 0;
+            constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * 48u;  // 3*kseg/8 chunks of 16 B per row, 128 B per 8 rows
+            constexpr int ksteps = 3 * kseg / 16;                       // K = 16 halves = two chunks per instruction
             const uint64_t descA0 = umma_desc(smem_u32(sA), lbo, sbo);
             const uint64_t descB0 = umma_desc(smem_u32(sB), lbo, sbo);
-            mbar_wait_bounded(a_full, 0);
+            mbar_wait_warp(a_full, 0);
+            int s = 0;
+            uint32_t full_par = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % S, n = t / S, buf = t & 1;
-                mbar_wait_bounded(&acc_empty[buf], (uint32_t)(((t >> 1) & 1) ^ 1));
-                mbar_wait_bounded(&full[s], (uint32_t)(n & 1));
-                tc_fence_after();
+                const int buf = t & 1;
+                const uint32_t par = (uint32_t)((t >> 1) & 1);
+                mbar_wait_warp(&full[s], full_par);
                 const uint64_t descB = descB0 + (uint64_t)(((uint32_t)s * b_bytes) >> 4);
 #pragma unroll
-                for (int rb = 0; rb < kTcRowBlocks; ++rb) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcRowBlocks * kTcN + rb * kTcN);
+                for (int rb = 0; rb < RB; ++rb) {
+                    // the two row blocks are committed separately: warpgroup 1 runs half a tile behind warpgroup 0,
+                    // so the two epilogue warps of a scheduler never sit at a tile boundary together
+                    mbar_wait_warp(&acc_empty[buf * RB + rb], par ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcAccCols + rb * NT);
                     const uint64_t descA = descA0 + (uint64_t)(((uint32_t)rb * a_bytes) >> 4);
-                    uint32_t accum = 0;
+                    if (elect_one()) {
+                        if (!skip_mma) {
 #pragma unroll
-                    for (int seg = 0; seg < 3; ++seg) {  // A_hi.B_hi, A_lo.B_hi, A_hi.B_lo
-                        const uint32_t offA = seg == 1 ? lo_off : 0u, offB = seg == 2 ? lo_off : 0u;
-                        for (int j = 0; j < ksteps; ++j) {
-                            umma_tf32(d_tmem, descA + (uint64_t)((offA + (uint32_t)j * 256u) >> 4),
-                                      descB + (uint64_t)((offB + (uint32_t)j * 256u) >> 4), idesc, accum);
-                            accum = 1;
+                            for (int j = 0; j < ksteps; ++j)
+                                umma_f16(d_tmem, descA + (uint64_t)(j * 16), descB + (uint64_t)(j * 16), idesc,
+                                         j > 0 ? 1u : 0u);
                         }
+                        umma_commit(&acc_full[buf * RB + rb]);
+                        if (rb == RB - 1) umma_commit(&empty[s]);  // the stage is free once these MMAs have read it
                     }
+                    __syncwarp();
                 }
-                umma_commit(&empty[s]);        // the stage is free once these MMAs have read it
-                umma_commit(&acc_full[buf]);   // both accumulators of this buffer are complete
+                if (++s == S) {
+                    s = 0;
+                    full_par ^= 1u;
+                }
             }
         }
     } else if (wid >= kTcEpiWarp0) {
-        // ===== epilogue: thread = one out row, exp2 and sum over the tile's 128 columns =====
+        // ===== epilogue: warpgroup wg drains row block wg; thread = one out row; exp2 + sum over 128 columns =====
         const int ew = wid - kTcEpiWarp0;
-        const int rb = ew >> 2, q = ew & 3;
+        const int wg = ew >> 2, q = ew & 3;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const bool skip_exp = (A.dbg & 2) != 0;
         uint32_t va[32], vb[32];
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
-            mbar_wait_bounded(&acc_full[buf], (uint32_t)((t >> 1) & 1));
+        const bool prof = (A.dbg & 8) != 0;
+        long long c_acc = 0, c_ld = 0, c_t0 = clock64(), c_x;
+#define TC_T0() if (prof) c_x = clock64()
+#define TC_T1(dst) if (prof) dst += clock64() - c_x
+        if (n_tiles > 0 && !skip_exp) {
+            mbar_wait_bounded(&acc_full[wg], 0);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTcRowBlocks * kTcN + rb * kTcN);
-            float tile_sum;
-            WOTB_TMEM_LD32(va, taddr);
-            WOTB_TMEM_WAIT32(va);
-            WOTB_TMEM_LD32(vb, taddr + 32);
-            tile_sum = tc_exp2_sum32(va);
-            WOTB_TMEM_WAIT32(vb);
-            WOTB_TMEM_LD32(va, taddr + 64);
-            tile_sum += tc_exp2_sum32(vb);
-            WOTB_TMEM_WAIT32(va);
-            WOTB_TMEM_LD32(vb, taddr + 96);
-            tile_sum += tc_exp2_sum32(va);
-            WOTB_TMEM_WAIT32(vb);
-            // every column of this buffer is in registers: hand the accumulators back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            tile_sum += tc_exp2_sum32(vb);
-            acc += (double)tile_sum;
+            WOTB_TMEM_LD32(va, tmem_base + lane_base + (uint32_t)(wg * NT));
         }
-        const long long row = o0 + rb * kTcM + q * 32 + lane;
-        A.part[(long long)blockIdx.y * A.out_ld + row] = acc;
+        for (int t0 = 0; t0 < n_tiles; t0 += 8) {
+            // fp32 across 8 tiles (1024 positive terms), then float64: the FP64 pipe stays out of the tile loop
+            float facc = 0.f;
+            const int t1 = min(t0 + 8, n_tiles);
+            for (int t = t0; t < t1; ++t) {
+                const int buf = t & 1;
+                const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTcAccCols + wg * NT);
+                if (skip_exp) {
+                    mbar_wait_bounded(&acc_full[buf * RB + wg], (uint32_t)((t >> 1) & 1));
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf * RB + wg]);
+                    continue;
+                }
+                float tile_sum;
+                TC_T0();
+                WOTB_TMEM_WAIT32(va);  // columns 0..31 (issued at the end of the previous tile)
+                TC_T1(c_ld);
+                WOTB_TMEM_LD32(vb, taddr + 32);
+                tile_sum = tc_exp2_sum32(va);
+                TC_T0();
+                WOTB_TMEM_WAIT32(vb);
+                TC_T1(c_ld);
+                WOTB_TMEM_LD32(va, taddr + 64);
+                tile_sum += tc_exp2_sum32(vb);
+                TC_T0();
+                WOTB_TMEM_WAIT32(va);
+                TC_T1(c_ld);
+                WOTB_TMEM_LD32(vb, taddr + 96);
+                tile_sum += tc_exp2_sum32(va);
+                TC_T0();
+                WOTB_TMEM_WAIT32(vb);
+                TC_T1(c_ld);
+                // every column of this accumulator is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf * RB + wg]);
+                if (t + 1 < n_tiles) {
+                    // first columns of the next tile while the last 32 of this one are evaluated
+                    const int nb = (t + 1) & 1;
+                    TC_T0();
+                    mbar_wait_bounded(&acc_full[nb * RB + wg], (uint32_t)(((t + 1) >> 1) & 1));
+                    TC_T1(c_acc);
+                    tc_fence_after();
+                    WOTB_TMEM_LD32(va, tmem_base + lane_base + (uint32_t)(nb * kTcAccCols + wg * NT));
+                }
+                tile_sum += tc_exp2_sum32(vb);
+                facc += tile_sum;
+            }
+            acc += (double)facc;
+        }
+        A.part[(long long)blockIdx.y * A.out_ld + o0 + wg * kTcM + q * 32 + lane] = acc;
+        if (prof && lane == 0) {
+            long long *dst = A.prof + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + ew) * 4;
+            dst[0] = clock64() - c_t0, dst[1] = c_acc, dst[2] = c_ld, dst[3] = n_tiles;
+        }
+#undef TC_T0
+#undef TC_T1
     }
     tc_fence_before();
     __threadfence();
@@ -403,7 +485,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-inline int tc_kseg(int d) { return (int)round_up(d + 2, 8); }
+inline int tc_kseg(int d) { return (int)round_up(d + 2, 16); }
 inline bool tc_supported(int d) { return tc_kseg(d) <= kTcMaxKseg; }
 
 struct TcPlan {
@@ -414,12 +496,12 @@ struct TcPlan {
 inline TcPlan tc_plan(int d) {
     TcPlan p;
     p.kseg = tc_kseg(d);
-    const size_t row_bytes = (size_t)p.kseg * 8;
-    const size_t a = (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes, tail = 256;
-    int s = (int)((kTcSmemLimit - a - tail) / b);
+    const size_t row_bytes = (size_t)p.kseg * 6;
+    const size_t a = (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes;
+    int s = (int)((kTcSmemLimit - a - kTcTail) / b);
     if (s > kTcMaxStages) s = kTcMaxStages;
     p.n_stages = s;
-    p.smem = a + (size_t)s * b + tail;
+    p.smem = a + (size_t)s * b + kTcTail;
     return p;
 }
 
@@ -444,14 +526,35 @@ inline int tc_segments(int sm_count, int out_blocks, int in_tiles, int *seg_tile
     return best;
 }
 
+template <int KSEG>
+inline int tc_configure_one(int bytes) {
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<false, KSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<true, KSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return WOTB_OK;
+}
+
 inline int tc_configure(const TcPlan &plan) {
-    static size_t configured = 0;
-    if (configured < plan.smem) {
-        WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
-        configured = plan.smem;
+    static size_t configured[3] = {0, 0, 0};
+    const int k = plan.kseg / 16 - 1;
+    if (configured[k] < plan.smem) {
+        const int bytes = (int)plan.smem;
+        if (plan.kseg == 16) WOTB_TRY(tc_configure_one<16>(bytes));
+        if (plan.kseg == 32) WOTB_TRY(tc_configure_one<32>(bytes));
+        if (plan.kseg == 48) WOTB_TRY(tc_configure_one<48>(bytes));
+        configured[k] = plan.smem;
     }
     return WOTB_OK;
+}
+
+template <bool COLPASS>
+inline void tc_launch(const TcPlan &plan, dim3 grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
+                      int mode, double *rowsum_out) {
+    if (plan.kseg == 16)
+        k_online_tc<COLPASS, 16><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
+    else if (plan.kseg == 32)
+        k_online_tc<COLPASS, 32><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
+    else
+        k_online_tc<COLPASS, 48><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
 }
 
 }  // namespace wotb
@@ -469,7 +572,9 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
                    const double *off_out, const double *off_in, int impl, int reps, double *sums, double *ms_per_pass) {
     WOTB_REQUIRE(ctx && x_out && x_in && off_out && off_in && sums, "NULL argument");
     WOTB_REQUIRE(n_out >= 1 && n_in >= 1 && d >= 1 && reps >= 1, "bad sizes");
-    WOTB_REQUIRE(impl == 0 || (impl == 1 && tc_supported(d)), "impl must be 0 (SIMT) or 1 (tcgen05, d <= 38)");
+    const int dbg = impl >> 4;
+    impl &= 15;
+    WOTB_REQUIRE(impl == 0 || (impl == 1 && tc_supported(d)), "impl: 0 SIMT FP32, 1 tcgen05 (d <= 46)");
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     wotb_params prm;
@@ -492,12 +597,12 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         return at;
     };
     float ms = 0.f;
-    if (impl == 1) {
+    if (impl >= 1) {
         const TcPlan plan = tc_plan(d);
         WOTB_TRY(tc_configure(plan));
         const int64_t po = round_up(n_out, kTcOut), pi = round_up(n_in, kTcOut);
-        const size_t row_bytes = (size_t)plan.kseg * 8;
-        const int out_blocks = (int)(po / kTcOut), in_tiles = (int)cdiv(n_in, kTcN);
+        const size_t row_bytes = (size_t)plan.kseg * 6;
+        const int out_blocks = (int)cdiv(n_out, kTcOut), in_tiles = (int)cdiv(n_in, kTcN);
         int seg_tiles = 0;
         const int nseg = tc_segments(ctx->sm_count, out_blocks, in_tiles, &seg_tiles);
         const size_t o_ao = take(po * row_bytes), o_bo = take(po * row_bytes), o_ai = take(pi * row_bytes),
@@ -505,11 +610,11 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
                      o_cnt = take((size_t)out_blocks * 4 + 64);
         WOTB_TRY(ctx->onl.reserve(off));
         char *ob = ctx->onl.as<char>();
-        float *Ao = (float *)(ob + o_ao), *Bo = (float *)(ob + o_bo), *Ai = (float *)(ob + o_ai), *Bi = (float *)(ob + o_bi);
+        __half *Ao = (__half *)(ob + o_ao), *Bo = (__half *)(ob + o_bo), *Ai = (__half *)(ob + o_ai), *Bi = (__half *)(ob + o_bi);
         double *resid = (double *)(ob + o_res), *part = (double *)(ob + o_part);
         unsigned int *cnt = (unsigned int *)(ob + o_cnt);
         WOTB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)out_blocks * 4, st));
-        const int cpr = plan.kseg / 4;
+        const int cpr = plan.kseg / 8;
         k_tc_pack<<<(unsigned)cdiv(po * cpr, 256), 256, 0, st>>>(x_out, (int)n_out, d, po, plan.kseg, Ao, Bo, nullptr, scale);
         k_tc_pack<<<(unsigned)cdiv(pi * cpr, 256), 256, 0, st>>>(x_in, (int)n_in, d, pi, plan.kseg, Ai, Bi, nullptr, scale);
         k_tc_slots<<<(unsigned)cdiv(n_out > n_in ? n_out : n_in, 256), 256, 0, st>>>(off_out, (int)n_out, Ao, resid, off_in,
@@ -517,11 +622,17 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         TcArgs A;
         A.opA = Ao, A.opB = Bi, A.resid = resid, A.out_n = (int)n_out, A.out_ld = po, A.kseg = plan.kseg;
         A.n_stages = plan.n_stages, A.nseg = nseg, A.seg_tiles = seg_tiles, A.part = part, A.counters = cnt;
-        A.out_blk0 = 0, A.in_tile0 = 0, A.in_ntiles = in_tiles;
+        A.out_blk0 = 0, A.in_tile0 = 0, A.in_ntiles = in_tiles, A.dbg = dbg;
+        A.prof = nullptr;
+        const size_t prof_n = (size_t)out_blocks * nseg * 8 * 4;
+        if (dbg & 8) {
+            WOTB_TRY(ctx->hTmp.reserve(prof_n * 8));
+            A.prof = ctx->hTmp.as<long long>();
+        }
         const dim3 grid(out_blocks, nseg);
-        k_online_tc<false><<<grid, kTcThreads, plan.smem, st>>>(A, V, d_ctrl, 4, sums);
+        tc_launch<false>(plan, grid, st, A, V, d_ctrl, 4, sums);
         WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
-        for (int r = 0; r < reps; ++r) k_online_tc<false><<<grid, kTcThreads, plan.smem, st>>>(A, V, d_ctrl, 4, sums);
+        for (int r = 0; r < reps; ++r) tc_launch<false>(plan, grid, st, A, V, d_ctrl, 4, sums);
         WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
     } else {
         const int64_t ldo = round_up(n_out, kOnTile), ldi = round_up(n_in, kOnTile);
@@ -561,6 +672,59 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     WOTB_CUDA(cudaGetLastError());
     WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_pass) *ms_per_pass = ms / reps;
+    if (impl == 1 && (dbg & 8)) {  // cycle counters of the last launch: mean over the epilogue warps
+        const size_t n = ctx->hTmp.cap / 8 < 8 * 4 * 65536 ? ctx->hTmp.cap / 8 : 8 * 4 * 65536;
+        std::vector<long long> hp(n);
+        WOTB_CUDA(cudaMemcpy(hp.data(), ctx->hTmp.ptr, n * 8, cudaMemcpyDeviceToHost));
+        double tot = 0, wa = 0, wl = 0, tiles = 0;
+        size_t warps = 0;
+        for (size_t w = 0; w + 3 < n; w += 4) {
+            if (hp[w + 3] <= 0 || hp[w + 3] > 100000) continue;
+            tot += hp[w], wa += hp[w + 1], wl += hp[w + 2], tiles += hp[w + 3];
+            ++warps;
+        }
+        if (warps) fprintf(stderr, "[tc prof] warps %zu tiles/warp %.1f | cycles per tile: total %.0f, waiting for accumulators %.0f, waiting for tcgen05.ld %.0f\n",
+                           warps, tiles / warps, tot / tiles, wa / tiles, wl / tiles);
+    }
+    return WOTB_OK;
+}
+
+// MUFU.EX2 peak of this GPU, measured: the roofline denominator of the online kernels (MEASURED_PEAKS.json has
+// HBM and tensor figures only).  16 independent ex2 chains per thread, 32 warps per SM, nothing else in the loop.
+__global__ void __launch_bounds__(1024) k_mufu_peak(float *out, int iters) {
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = -1.f - 0.001f * (float)(threadIdx.x + e);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = ex2_approx(v[e]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) s += v[e];
+    if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+
+int bench_mufu(wotb_ctx *ctx, double *ex2_per_s) {
+    WOTB_REQUIRE(ctx && ex2_per_s, "NULL argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    WOTB_TRY(ctx->hTmp.reserve(256));
+    const int iters = 4096, blocks = ctx->sm_count * 2;
+    k_mufu_peak<<<blocks, 1024, 0, st>>>(ctx->hTmp.as<float>(), 64);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
+        k_mufu_peak<<<blocks, 1024, 0, st>>>(ctx->hTmp.as<float>(), iters);
+        WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
+        WOTB_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double rate = (double)blocks * 1024.0 * 16.0 * iters / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    WOTB_CUDA(cudaGetLastError());
+    *ex2_per_s = best;
     return WOTB_OK;
 }
 
