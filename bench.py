@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every day by this factor (debugging)")
-    ap.add_argument("--kernel", default="stored", choices=["stored", "online"])
+    ap.add_argument("--kernel", default="stored", choices=["stored", "online", "online_simt"])
     ap.add_argument("--cpu-cells", type=int, default=2200, help="cells/day of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -168,12 +168,13 @@ def run_reference(args, rank, world):
 class DevicePair:
     """One day-pair on the device, driven through the device-pointer C ABI."""
 
-    def __init__(self, ctx, torch, max_i, max_j):
+    def __init__(self, ctx, torch, max_i, max_j, kernel="stored"):
         from wot_b200 import _lib
         self.ctx, self.torch, self.lib, self._lib = ctx, torch, ctx.lib, _lib
+        self.kernel = kernel
         dev = "cuda:%d" % ctx.device
         self.ld_max = (max_j + 31) // 32 * 32
-        self.C = torch.empty(max_i * self.ld_max, dtype=torch.float32, device=dev)
+        self.C = torch.empty(max_i * self.ld_max if kernel == "stored" else 32, dtype=torch.float32, device=dev)
         self.out = torch.empty(max_i * max_j, dtype=torch.float64, device=dev)
         self.x0 = torch.empty(max_i * D, dtype=torch.float64, device=dev)
         self.x1 = torch.empty(max_j * D, dtype=torch.float64, device=dev)
@@ -198,19 +199,29 @@ class DevicePair:
         med = C.c_double()
         P = lambda tns: C.c_void_p(tns.data_ptr())  # noqa: E731
         L.check(lib.wotb_cost_median_dev(h, P(self.x0), I, P(self.x1), J, D, None, C.byref(med)))
-        L.check(lib.wotb_cost_matrix_dev(h, P(self.x0), I, P(self.x1), J, D, None, med.value, P(self.C), ld, L.F32))
+        online = self.kernel != "stored"
+        if not online:
+            L.check(lib.wotb_cost_matrix_dev(h, P(self.x0), I, P(self.x1), J, D, None, med.value, P(self.C), ld, L.F32))
         self.G[:I].copy_(self.G0)
         infos = []
         for it in range(GROWTH_ITERS):
             if it > 0:
                 self.G[:I].copy_(self.rows[:I])
             info = L.Info()
-            L.check(lib.wotb_sinkhorn_stored_dev(h, P(self.C), ld, I, J, P(self.G), C.byref(prm), P(self.f),
-                                                 P(self.g), P(self.rows), C.byref(info)))
+            if online:
+                L.check(lib.wotb_sinkhorn_online_dev(h, P(self.x0), I, P(self.x1), J, D, med.value, P(self.G),
+                                                     C.byref(prm), P(self.f), P(self.g), P(self.rows), C.byref(info)))
+            else:
+                L.check(lib.wotb_sinkhorn_stored_dev(h, P(self.C), ld, I, J, P(self.G), C.byref(prm), P(self.f),
+                                                     P(self.g), P(self.rows), C.byref(info)))
             infos.append(info.as_dict())
         last = infos[-1]
-        L.check(lib.wotb_coupling_dev(h, P(self.C), ld, I, J, P(self.f), P(self.g), last["eps_final"],
-                                      last["out_scale"], P(self.out), J, L.F64, None))
+        if online:
+            L.check(lib.wotb_coupling_online_dev(h, P(self.x0), I, P(self.x1), J, D, med.value, P(self.f), P(self.g),
+                                                 last["eps_final"], last["out_scale"], P(self.out), J, L.F64, None))
+        else:
+            L.check(lib.wotb_coupling_dev(h, P(self.C), ld, I, J, P(self.f), P(self.g), last["eps_final"],
+                                          last["out_scale"], P(self.out), J, L.F64, None))
         return infos
 
 
@@ -245,7 +256,9 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream()
     ctx = _lib.Context(local_rank, stream.cuda_stream)
     _lib._contexts[local_rank] = ctx
-    prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_STORED, **DEFAULTS)
+    online = args.kernel != "stored"
+    prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_ONLINE if online else _lib.KERNEL_STORED,
+                           online_simt=args.kernel == "online_simt", **DEFAULTS)
 
     pairs = synthetic.atlas_pairs(seed=1, scale=args.scale)
     n_pairs = len(pairs)
@@ -278,7 +291,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- leg 1: inputs resident in HBM, CUDA events on the library's stream ---------------------
-    dp = DevicePair(ctx, torch, max_i, max_j)
+    dp = DevicePair(ctx, torch, max_i, max_j, args.kernel)
     for s in range(args.warmup):
         dp.load(*coords[mine[s]])
         dp.run(prm)
@@ -329,7 +342,7 @@ def run_ours(args, rank, world, local_rank):
     def e2e_step(p):
         x0, x1, g = pin_in[p]
         view = out[: p[0] * p[1]].reshape(p[0], p[1])
-        wot_ot.solve_coords(x0, x1, g, _lib.SOLVER_DUALITY_GAP, growth_iters=GROWTH_ITERS, kernel="stored",
+        wot_ot.solve_coords(x0, x1, g, _lib.SOLVER_DUALITY_GAP, growth_iters=GROWTH_ITERS, kernel=args.kernel,
                             out=view, device=local_rank, **DEFAULTS)
 
     e2e_step(mine[0])                        # warm the pinned bounce paths and workspaces
@@ -395,7 +408,7 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 K / f64 potentials",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "solver": "duality_gap", "kernel": "stored", "eps": 0.05, "lambda1": 1,
+        "config": {"workload": WORKLOAD, "solver": "duality_gap", "kernel": args.kernel, "eps": 0.05, "lambda1": 1,
                    "lambda2": 50, "l2": "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)",
                    "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale},
         "sinkhorn_iters_per_s": iters_all / t_dev,

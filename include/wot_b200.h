@@ -43,7 +43,8 @@ enum wotb_solver {
 
 enum wotb_kernel {
     WOTB_KERNEL_STORED = 0, /* K = exp((u-C+v)/eps) kept in HBM as fp32; matvecs are HBM-bound   */
-    WOTB_KERNEL_ONLINE = 1  /* K recomputed tile by tile from coordinates; FP32/MUFU-bound        */
+    WOTB_KERNEL_ONLINE = 1  /* K recomputed tile by tile from coordinates (tcgen05 exponent + MUFU.EX2 epilogue
+                               for d <= 46, SIMT FP32 otherwise); MUFU-bound                       */
 };
 
 enum wotb_status {
@@ -70,7 +71,8 @@ typedef struct wotb_params {
     int32_t solver; /* enum wotb_solver */
     int32_t kernel; /* enum wotb_kernel */
     int32_t use_graph; /* 1: replay the per-batch launch sequence as a CUDA graph */
-    int32_t reserved;  /* flags; bit0 = 1 disables the fused one-sweep iteration kernel (two matvec kernels instead) */
+    int32_t reserved;  /* flags; bit0 = 1 disables the fused one-sweep iteration kernel (two matvec kernels instead);
+                          bit1 = 1 runs the online kernel on the SIMT FP32 pass instead of the tcgen05 pass */
 } wotb_params;
 
 /* What the reference keeps as locals of the solver; returned for the parity criteria. */

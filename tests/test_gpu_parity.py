@@ -221,9 +221,10 @@ def test_fixed_point_property_large(ot):
 # ---------------------------------------------------------------------------------------------------
 # online kernel (K recomputed from coordinates, never stored)
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["online", "online_simt"])
 @pytest.mark.parametrize("shape,d", [((1500, 1637), 30), ((2000, 2000), 30), ((700, 3001), 30), ((3001, 700), 30),
-                                     ((900, 1000), 5), ((600, 650), 50), ((130, 129), 33)])
-def test_online_kernel_vs_oracle(ot, shape, d):
+                                     ((900, 1000), 5), ((600, 650), 50), ((130, 129), 33), ((257, 5000), 30)])
+def test_online_kernel_vs_oracle(ot, shape, d, kernel):
     """exp((f_i + g_j - C_ij)/eps) recomputed tile by tile: same couplings, potentials and batch counts."""
     from oracle import wot_oracle as orc
     from wot_b200 import synthetic
@@ -233,16 +234,19 @@ def test_online_kernel_vs_oracle(ot, shape, d):
     want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
                                              gap="marginal", **DEFAULTS)
     tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
-                                          G=growth.copy(), kernel="online", **DEFAULTS)
+                                          G=growth.copy(), kernel=kernel, **DEFAULTS)
     rep = assert_coupling_close(tmap, want)
     got = ot.last_solve_info()
     _check_potentials(got, info.f, info.g, 0.05)
-    assert got["infos"][0]["batches"][:5] == info.batches[:5], rep
-    assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+    # batch counts within +-1 per stage (north_star).  The warm-stage criterion (:158-160) is a 1e-6 threshold on the
+    # change of the iterates, so the ~1e-5 exponent error of the online kernels can move a crossing by one batch.
+    batches = got["infos"][0]["batches"]
+    assert all(abs(batches[k] - info.batches[k]) <= 1 for k in range(6)), (batches, info.batches, rep)
     np.testing.assert_allclose(got["learned_growth"][-1], want.sum(axis=1), rtol=RTOL)
 
 
-def test_online_kernel_growth_scale_and_fixed_iters(ot):
+@pytest.mark.parametrize("kernel", ["online", "online_simt"])
+def test_online_kernel_growth_scale_and_fixed_iters(ot, kernel):
     from oracle import wot_oracle as orc
     from wot_b200 import synthetic
     x0, x1, growth = synthetic.day_pair_coords(500, 560, d=30, seed=77)
@@ -251,11 +255,35 @@ def test_online_kernel_growth_scale_and_fixed_iters(ot):
     params = dict(DEFAULTS, growth_iters=2)
     want, learned = orc.compute_transport_matrix(orc.optimal_transport_duality_gap, C=cost, G=growth.copy(), **params)
     tmap, got_learned = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, sv), C=None,
-                                                    G=growth.copy(), kernel="online", **params)
+                                                    G=growth.copy(), kernel=kernel, **params)
     assert_coupling_close(tmap, want)
     np.testing.assert_allclose(np.array(got_learned), np.array(learned), rtol=RTOL)
     short = dict(DEFAULTS, scaling_iter=330, extra_iter=40, inner_iter_max=50)
     want = orc.transport_stablev2(C=cost, G=growth, **short)
     tmap, _ = ot.compute_transport_matrix(ot.transport_stablev2, coords=(x0, x1, sv), C=None, G=growth.copy(),
-                                          kernel="online", **short)
+                                          kernel=kernel, **short)
     assert_coupling_close(tmap, want)
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("shape,d", [((300, 340), 30), ((3000, 3301), 30), ((700, 2500), 12), ((1111, 777), 40)])
+def test_online_pass_kernels_vs_numpy(impl, shape, d):
+    """One online-kernel pass, sums[i] = sum_j exp2(off_out_i + off_in_j + scale^2 <x_i, y_j>), against float64
+    NumPy: the SIMT FP32 kernel (impl 0) and the tcgen05 kernel with 8 / 16 epilogue warps (impl 1 / 2).
+    Exponent error budget ~1e-5 (3-term fp16 split / fp32 dot product) -> row sums within 5e-5."""
+    import ctypes as C
+    import torch
+    from tools.online_pass_check import make_inputs, reference
+    from wot_b200 import _lib
+    n_out, n_in = shape
+    x0, x1, scale, off_out, off_in = make_inputs(n_out, n_in, d, seed=n_out + d)
+    want = reference(x0, x1, scale, off_out, off_in)
+    ctx = _lib.context(0)
+    dev = "cuda:%d" % ctx.device
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x0, x1, off_out, off_in)]
+    sums = torch.empty(n_out, dtype=torch.float64, device=dev)
+    P = lambda v: C.c_void_p(v.data_ptr())  # noqa: E731
+    _lib.check(ctx.lib.wotb_online_rowsums_dev(ctx.handle, P(t[0]), n_out, P(t[1]), n_in, d, float(scale), P(t[2]),
+                                               P(t[3]), impl, 1, P(sums), None))
+    got = sums.cpu().numpy()
+    assert np.max(np.abs(got - want) / want) <= 5e-5

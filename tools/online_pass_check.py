@@ -59,9 +59,10 @@ def main():
     import torch
     ctx = _lib.context(0)
     impls = [int(v) for v in args.impls.split(",")]
-    names = {0: "simt", 1: "tcgen05"}
+    names = {0: "simt", 1: "tcgen05 ew4", 2: "tcgen05 ew8"}
     for dbg in range(1, 16):
-        names[1 + 16 * dbg] = "tcgen05" + "".join(t for b, t in ((1, " no-mma"), (2, " no-exp"), (8, " prof")) if dbg & b)
+        for base in (1, 2):
+            names[base + 16 * dbg] = names[base] + "".join(t for b, t in ((1, " no-mma"), (2, " no-exp"), (8, " prof")) if dbg & b)
     peak = C.c_double()
     _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak)))
     print("MUFU.EX2 peak (measured): %.3f T ex2/s" % (peak.value / 1e12), flush=True)

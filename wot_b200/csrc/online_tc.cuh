@@ -45,28 +45,12 @@ constexpr int kTcRowBlocks = 2;           // A blocks per CTA
 constexpr int kTcOut = kTcM * kTcRowBlocks;  // row padding of every operand array
 constexpr int kTcN = 128;                 // in-side rows per B tile (UMMA N)
 constexpr int kTcAccCols = kTcRowBlocks * kTcN;  // TMEM columns per accumulator buffer (two buffers = all 512)
-constexpr int kTcTail = 2048;             // barriers + reduction scratch after the operand stages
+constexpr int kTcTail = 4096;             // barriers + reduction scratch after the operand stages
 constexpr int kTcMaxStages = 6;
-constexpr int kTcThreads = 384;
 constexpr int kTcEpiWarp0 = 4;            // first epilogue warp (multiple of 4: warp % 4 selects the TMEM lane quadrant)
 constexpr int kTcMaxKseg = 48;            // d <= 46
 constexpr int kTcTmemCols = 512;
-constexpr float kTcPad = -60000.f;        // offset of padded in rows (finite in fp16): exp2 underflows to exactly 0
 constexpr int kTcSmemLimit = 232448;
-
-// half-precision element k (0 <= k < 3*kseg: the three segments) of row r; kc = 16-byte chunks per row = 3*kseg/8
-__host__ __device__ __forceinline__ long long tc_index(long long r, int k, int kc) {
-    return ((r >> 3) * kc + (k >> 3)) * 64 + (r & 7) * 8 + (k & 7);
-}
-
-constexpr float kTcLoScale = 2048.f;              // 2^11
-constexpr float kTcLoInv = 1.f / 2048.f;
-
-// x = hi + 2^-11 lo' with hi, lo' in fp16 (round to nearest).  |x| must stay below the fp16 range (6.5e4).
-__device__ __forceinline__ void tc_split(double x, __half &hi, __half &lo) {
-    hi = __double2half(x);
-    lo = __double2half((x - (double)__half2float(hi)) * 2048.0);
-}
 
 // ---- operand preparation ------------------------------------------------------------------------
 // Coordinates (scaled for the current epsilon) into both operand roles of one side.
@@ -112,11 +96,19 @@ __global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long 
 }
 
 // Exponent offsets into the spare K slots: the out side's static offsets into its A-role rows (+ the
-// float64 residual), the in side's current offsets into its B-role rows.  Runs before every pass.
+// float64 residual), the in side's current offsets into its B-role rows.  During the iterations the in-side
+// slots are kept current by the finishing code (tc_store_in_offset); this kernel runs when everything changed.
 __global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half *__restrict__ opA_out,
                            double *__restrict__ resid, const double *__restrict__ off_in, int n_in,
-                           __half *__restrict__ opB_in, int kseg, const SolveCtrl *ctrl) {
-    if (ctrl && ctrl->done) return;
+                           __half *__restrict__ opB_in, int kseg, const SolveCtrl *ctrl, int gate) {
+    // gate 0: unless the solve is done; 1: only when need_build is set (the offsets were rewritten by an absorption,
+    // an epsilon change or the initialisation); 3: only for the S0 pass of the final stage; -1: always
+    if (ctrl && gate >= 0) {
+        if (ctrl->done) return;
+        if (gate == 1 && !ctrl->need_build) return;
+        if (gate == 3 && (!ctrl->need_build || ctrl->solver != WOTB_SOLVER_DUALITY_GAP || ctrl->stage != WOTB_N_STAGES - 1))
+            return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int kc = 3 * (kseg >> 3);
     if (i < n_out) {
@@ -228,24 +220,39 @@ struct TcArgs {
     const __half *opB;    // in side, B role (rows padded to kTcOut)
     const double *resid;  // out side: float64 residual of the static offsets
     int out_n;            // valid out entries
-    long long out_ld;     // stride of the partial-sum rows (>= padded out rows)
-    int kseg;             // K elements per segment (multiple of 16, >= d + 2)
-    int n_stages;         // B ring depth
-    int nseg;             // segments of the in side (grid.y)
-    int seg_tiles;        // B tiles per segment
-    double *part;         // [nseg][out_ld] partial sums
-    unsigned int *counters;  // one per out block
-    int out_blk0;         // first out block (RB * 128 rows) of this launch
-    int in_tile0;         // first in tile (NT rows) that is reduced over
+    long long out_ld;     // stride of the partial-sum slots (>= padded out rows)
+    int n_blocks;         // out blocks (256 rows) of this launch
+    int out_blk0;         // first out block of this launch
+    int in_tile0;         // first in tile (128 rows) that is reduced over
     int in_ntiles;        // number of in tiles reduced over
+    int n_stages;         // B ring depth
+    double *part;         // [slots][out_ld] partial sums, one slot per CTA that contributes to an out block
+    unsigned int *counters;  // one per out block
     int dbg;              // measurement only: bit0 skip the MMAs, bit1 skip the exp2 work, bit3 write cycle counters
-    long long *prof;      // [CTA][8 epilogue warps][4]: cycles total, waiting for accumulators, waiting for tcgen05.ld, tiles
+    long long *prof;      // [CTA][epilogue warp][4]: cycles total, waiting for accumulators, waiting for tcgen05.ld, tiles
 };
 
+// The CTA that owns work unit g when T units are dealt to G CTAs in contiguous ranges [c T / G, (c + 1) T / G).
+__host__ __device__ __forceinline__ int tc_cta_of_unit(long long g, long long T, int G) {
+    return (int)(((g + 1) * G + T - 1) / T - 1);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// One pass = (out blocks) x (in tiles) work units of 256 x 128 entries, dealt to the CTAs of a one-wave
+// grid in contiguous ranges (block-major), "stream-K" style: every SM gets the same number of units whatever
+// the shape, and the per-CTA fixed cost (TMEM allocation, barrier setup, pipeline fill) is paid once.  A CTA's
+// range may cross out-block boundaries; the A blocks are double buffered so the switch costs nothing.  Each
+// (out block, CTA) pair writes its partial row sums into its own slot; the last CTA to arrive at an out block
+// adds the slots in slot order and applies the update, so the result does not depend on timing.
+//
 // modes as in k_online_pass: 0 half-step, 1 row sums for the gap, 2 coupling row sums, 3 S0 partials,
-// 4 partial sums only (row-sharded solves)
-template <bool COLPASS, int KSEG>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// 4 partial sums only (row-sharded solves).  EW = epilogue warps per row block (4: thread = row x 128 columns,
+// 8: thread = row x 64 columns).
+template <bool COLPASS, int KSEG, int EW>
+__global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     k_online_tc(TcArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
     if (mode == 0 || mode == 4) {
         if (!iteration_active(ctrl)) return;
@@ -257,27 +264,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             return;
     }
     constexpr int RB = kTcRowBlocks, NT = kTcN;
-    extern __shared__ __align__(128) unsigned char tc_smem[];
-    __shared__ int is_last;
-    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    constexpr int kEpiThreads = RB * EW * 32;
+    constexpr int NCH = 4 / (EW / 4);  // 32-column chunks per tile and warp
     constexpr int kseg = KSEG;
     constexpr uint32_t row_bytes = (uint32_t)kseg * 6u;  // 3 * kseg halves
     constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int S = A.n_stages;
-    unsigned char *sA = tc_smem;
-    unsigned char *sB = sA + RB * a_bytes;
+    unsigned char *sA = tc_smem;                      // [2 buffers][RB blocks]
+    unsigned char *sB = sA + 2 * RB * a_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)S * b_bytes);
     uint64_t *empty = full + kTcMaxStages;
     uint64_t *acc_full = empty + kTcMaxStages;  // [buffer][row block]
     uint64_t *acc_empty = acc_full + 2 * RB;
-    uint64_t *a_full = acc_empty + 2 * RB;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
+    uint64_t *a_full = acc_empty + 2 * RB;      // [A buffer]
+    uint64_t *a_empty = a_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 2);
+    double *red = reinterpret_cast<double *>(full) + 32;  // [RB * 128]: second column half of every row (EW == 8)
 
-    const int out_blk = blockIdx.x + A.out_blk0;
-    const long long o0 = (long long)out_blk * kTcOut;
-    const int t_begin = A.in_tile0 + blockIdx.y * A.seg_tiles;
-    const int t_end = min(A.in_tile0 + A.in_ntiles, t_begin + A.seg_tiles);
-    const int n_tiles = max(t_end - t_begin, 0);
+    const int nt = A.in_ntiles;
+    const long long T = (long long)A.n_blocks * nt;
+    const int G = gridDim.x;
+    const long long g0 = (long long)blockIdx.x * T / G, g1 = (long long)(blockIdx.x + 1) * T / G;
+    const int b_first = (int)(g0 / nt), t_first = (int)(g0 - (long long)b_first * nt);
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -286,9 +297,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         for (int b = 0; b < 2 * RB; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);  // the four warps of the warpgroup that drains it
+            mbar_init(&acc_empty[b], EW);  // the warps that drain it
         }
-        mbar_init(a_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&a_full[b], 1);
+            mbar_init(&a_empty[b], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -303,50 +317,62 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
-    double acc = 0.0;  // epilogue threads: the row sum of this CTA's segment
     if (wid == 0) {
-        if (lane == 0 && n_tiles > 0) {
-            // ===== TMA producer: the two A blocks once, then the B ring =====
-            mbar_expect_tx(a_full, RB * a_bytes);
-            const unsigned char *srcA = reinterpret_cast<const unsigned char *>(A.opA) + (size_t)o0 * row_bytes;
-            for (int rb = 0; rb < RB; ++rb)
-                bulk_g2s(sA + rb * a_bytes, srcA + (size_t)rb * a_bytes, a_bytes, a_full);
+        if (lane == 0) {
+            // ===== TMA producer: per out-block segment the two A blocks, then the B ring =====
+            const unsigned char *srcA = reinterpret_cast<const unsigned char *>(A.opA);
             const unsigned char *srcB = reinterpret_cast<const unsigned char *>(A.opB);
-            for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % S, n = t / S;
-                mbar_wait_bounded(&empty[s], (uint32_t)((n & 1) ^ 1));
-                mbar_expect_tx(&full[s], b_bytes);
-                bulk_g2s(sB + (size_t)s * b_bytes, srcB + (size_t)(t_begin + t) * b_bytes, b_bytes, &full[s]);
+            int s = 0, seg = 0, b = b_first, t = t_first;
+            uint32_t empty_par = 1;
+            for (long long g = g0; g < g1; ++seg, ++b, t = 0) {
+                const int abuf = seg & 1;
+                mbar_wait_bounded(&a_empty[abuf], (uint32_t)(((seg >> 1) & 1) ^ 1));
+                mbar_expect_tx(&a_full[abuf], RB * a_bytes);
+                const unsigned char *blockA = srcA + (size_t)(A.out_blk0 + b) * (RB * a_bytes);
+                for (int rb = 0; rb < RB; ++rb)
+                    bulk_g2s(sA + (abuf * RB + rb) * a_bytes, blockA + (size_t)rb * a_bytes, a_bytes, &a_full[abuf]);
+                const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+                for (int k = 0; k < n_in_seg; ++k) {
+                    mbar_wait_bounded(&empty[s], empty_par);
+                    mbar_expect_tx(&full[s], b_bytes);
+                    bulk_g2s(sB + (size_t)s * b_bytes, srcB + (size_t)(A.in_tile0 + t + k) * b_bytes, b_bytes, &full[s]);
+                    if (++s == S) {
+                        s = 0;
+                        empty_par ^= 1u;
+                    }
+                }
+                g += n_in_seg;
             }
         }
     } else if (wid == 1) {
-        if (n_tiles > 0) {
-            // ===== MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected
-            // lane issues.  Issue-side cost matters: with per-lane descriptor arithmetic the issuing thread, not
-            // the tensor pipe, bounded the pass (~100 clocks per instruction, measured) =====
-            // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N, M
-            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-            const bool skip_mma = (A.dbg & 1) != 0;
-            constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * 48u;  // 3*kseg/8 chunks of 16 B per row, 128 B per 8 rows
-            constexpr int ksteps = 3 * kseg / 16;                       // K = 16 halves = two chunks per instruction
-            const uint64_t descA0 = umma_desc(smem_u32(sA), lbo, sbo);
-            const uint64_t descB0 = umma_desc(smem_u32(sB), lbo, sbo);
-            mbar_wait_warp(a_full, 0);
-            int s = 0;
-            uint32_t full_par = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int buf = t & 1;
-                const uint32_t par = (uint32_t)((t >> 1) & 1);
+        // ===== MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected
+        // lane issues.  Issue-side cost matters: with per-lane descriptor arithmetic the issuing thread, not
+        // the tensor pipe, bounded the pass (~100 clocks per instruction, measured) =====
+        // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N, M
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+        const bool skip_mma = (A.dbg & 1) != 0;
+        constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * 48u;  // 3*kseg/8 chunks of 16 B per row, 128 B per 8 rows
+        constexpr int ksteps = 3 * kseg / 16;                       // K = 16 halves = two chunks per instruction
+        const uint64_t descA0 = umma_desc(smem_u32(sA), lbo, sbo);
+        const uint64_t descB0 = umma_desc(smem_u32(sB), lbo, sbo);
+        int s = 0, seg = 0, t = t_first;
+        uint32_t full_par = 0, u = 0;
+        for (long long g = g0; g < g1; ++seg, t = 0) {
+            const int abuf = seg & 1;
+            mbar_wait_warp(&a_full[abuf], (uint32_t)((seg >> 1) & 1));
+            const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+            for (int k = 0; k < n_in_seg; ++k, ++u) {
+                const uint32_t buf = u & 1u, par = (u >> 1) & 1u;
                 mbar_wait_warp(&full[s], full_par);
                 const uint64_t descB = descB0 + (uint64_t)(((uint32_t)s * b_bytes) >> 4);
 #pragma unroll
                 for (int rb = 0; rb < RB; ++rb) {
-                    // the two row blocks are committed separately: warpgroup 1 runs half a tile behind warpgroup 0,
-                    // so the two epilogue warps of a scheduler never sit at a tile boundary together
+                    // the two row blocks are committed separately: the warps of row block 1 run half a tile behind
+                    // those of row block 0, so the epilogue warps of a scheduler do not sit at a tile boundary together
                     mbar_wait_warp(&acc_empty[buf * RB + rb], par ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcAccCols + rb * NT);
-                    const uint64_t descA = descA0 + (uint64_t)(((uint32_t)rb * a_bytes) >> 4);
+                    const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
                     if (elect_one()) {
                         if (!skip_mma) {
 #pragma unroll
@@ -355,7 +381,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                          j > 0 ? 1u : 0u);
                         }
                         umma_commit(&acc_full[buf * RB + rb]);
-                        if (rb == RB - 1) umma_commit(&empty[s]);  // the stage is free once these MMAs have read it
+                        if (rb == RB - 1) {
+                            umma_commit(&empty[s]);                             // the stage is free once these MMAs have read it
+                            if (k == n_in_seg - 1) umma_commit(&a_empty[abuf]);  // and so are the A blocks of this segment
+                        }
                     }
                     __syncwarp();
                 }
@@ -364,123 +393,144 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     full_par ^= 1u;
                 }
             }
+            g += n_in_seg;
         }
     } else if (wid >= kTcEpiWarp0) {
-        // ===== epilogue: warpgroup wg drains row block wg; thread = one out row; exp2 + sum over 128 columns =====
+        // ===== epilogue: thread = one out row x (128 / (EW / 4)) columns of every tile; exp2 + in-thread sum =====
         const int ew = wid - kTcEpiWarp0;
-        const int wg = ew >> 2, q = ew & 3;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int rb = ew / EW, within = ew % EW;
+        const int q = within & 3, h = within >> 2;
+        const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32));
         const bool skip_exp = (A.dbg & 2) != 0;
-        uint32_t va[32], vb[32];
         const bool prof = (A.dbg & 8) != 0;
-        long long c_acc = 0, c_ld = 0, c_t0 = clock64(), c_x;
+        long long c_acc = 0, c_ld = 0, c_t0 = clock64(), c_x = 0, c_pro = 0, c_fin = 0;
 #define TC_T0() if (prof) c_x = clock64()
 #define TC_T1(dst) if (prof) dst += clock64() - c_x
-        if (n_tiles > 0 && !skip_exp) {
-            mbar_wait_bounded(&acc_full[wg], 0);
+        uint32_t va[32], vb[32];
+        const uint32_t n_units = (uint32_t)(g1 - g0);
+        if (!skip_exp) {
+            mbar_wait_bounded(&acc_full[rb], 0);
             tc_fence_after();
-            WOTB_TMEM_LD32(va, tmem_base + lane_base + (uint32_t)(wg * NT));
+            WOTB_TMEM_LD32(va, tmem_base + lane_col);
+            if (prof) c_pro = clock64() - c_t0;
         }
-        for (int t0 = 0; t0 < n_tiles; t0 += 8) {
-            // fp32 across 8 tiles (1024 positive terms), then float64: the FP64 pipe stays out of the tile loop
-            float facc = 0.f;
-            const int t1 = min(t0 + 8, n_tiles);
-            for (int t = t0; t < t1; ++t) {
-                const int buf = t & 1;
-                const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTcAccCols + wg * NT);
-                if (skip_exp) {
-                    mbar_wait_bounded(&acc_full[buf * RB + wg], (uint32_t)((t >> 1) & 1));
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[buf * RB + wg]);
-                    continue;
+        int seg = 0, b = b_first, t = t_first;
+        uint32_t u = 0;
+        for (long long g = g0; g < g1; ++seg, ++b, t = 0) {
+            const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+            double acc = 0.0;
+            for (int k0 = 0; k0 < n_in_seg; k0 += 8) {
+                // fp32 across 8 tiles (<= 1024 positive terms), then float64: the FP64 pipe stays out of the tile loop
+                float facc = 0.f;
+                const int k1 = min(k0 + 8, n_in_seg);
+                for (int k = k0; k < k1; ++k, ++u) {
+                    const uint32_t buf = u & 1u;
+                    const uint32_t taddr = tmem_base + lane_col + buf * kTcAccCols;
+                    if (skip_exp) {
+                        mbar_wait_bounded(&acc_full[buf * RB + rb], (u >> 1) & 1u);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf * RB + rb]);
+                        continue;
+                    }
+                    float tile_sum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NCH; c += 2) {
+                        TC_T0();
+                        WOTB_TMEM_WAIT32(va);  // chunk c (issued one step earlier)
+                        TC_T1(c_ld);
+                        WOTB_TMEM_LD32(vb, taddr + (c + 1) * 32);
+                        tile_sum += tc_exp2_sum32(va);
+                        TC_T0();
+                        WOTB_TMEM_WAIT32(vb);
+                        TC_T1(c_ld);
+                        if (c + 2 < NCH) {
+                            WOTB_TMEM_LD32(va, taddr + (c + 2) * 32);
+                        } else {
+                            // every column of this accumulator is in registers: hand it back to the MMA warp, and
+                            // fetch the first columns of the next unit while the last 32 of this one are evaluated
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[buf * RB + rb]);
+                            if (u + 1 < n_units) {
+                                const uint32_t nb = (u + 1) & 1u;
+                                TC_T0();
+                                mbar_wait_bounded(&acc_full[nb * RB + rb], ((u + 1) >> 1) & 1u);
+                                TC_T1(c_acc);
+                                tc_fence_after();
+                                WOTB_TMEM_LD32(va, tmem_base + lane_col + nb * kTcAccCols);
+                            }
+                        }
+                        tile_sum += tc_exp2_sum32(vb);
+                    }
+                    facc += tile_sum;
                 }
-                float tile_sum;
-                TC_T0();
-                WOTB_TMEM_WAIT32(va);  // columns 0..31 (issued at the end of the previous tile)
-                TC_T1(c_ld);
-                WOTB_TMEM_LD32(vb, taddr + 32);
-                tile_sum = tc_exp2_sum32(va);
-                TC_T0();
-                WOTB_TMEM_WAIT32(vb);
-                TC_T1(c_ld);
-                WOTB_TMEM_LD32(va, taddr + 64);
-                tile_sum += tc_exp2_sum32(vb);
-                TC_T0();
-                WOTB_TMEM_WAIT32(va);
-                TC_T1(c_ld);
-                WOTB_TMEM_LD32(vb, taddr + 96);
-                tile_sum += tc_exp2_sum32(va);
-                TC_T0();
-                WOTB_TMEM_WAIT32(vb);
-                TC_T1(c_ld);
-                // every column of this accumulator is in registers: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[buf * RB + wg]);
-                if (t + 1 < n_tiles) {
-                    // first columns of the next tile while the last 32 of this one are evaluated
-                    const int nb = (t + 1) & 1;
-                    TC_T0();
-                    mbar_wait_bounded(&acc_full[nb * RB + wg], (uint32_t)(((t + 1) >> 1) & 1));
-                    TC_T1(c_acc);
-                    tc_fence_after();
-                    WOTB_TMEM_LD32(va, tmem_base + lane_base + (uint32_t)(nb * kTcAccCols + wg * NT));
-                }
-                tile_sum += tc_exp2_sum32(vb);
-                facc += tile_sum;
+                acc += (double)facc;
             }
-            acc += (double)facc;
+            g += n_in_seg;
+            // ---- this CTA's share of out block b is complete: publish it, and finish the block if it is the last ----
+            TC_T0();
+            const int blk = A.out_blk0 + b;
+            const long long row = (long long)blk * kTcOut + rb * kTcM + q * 32 + lane;
+            const int c_first = tc_cta_of_unit((long long)b * nt, T, G);
+            const int c_last = tc_cta_of_unit((long long)(b + 1) * nt - 1, T, G);
+            if (EW == 8) {
+                if (h == 1) red[rb * kTcM + q * 32 + lane] = acc;
+                named_bar_sync(1, kEpiThreads);
+                if (h == 0) acc += red[rb * kTcM + q * 32 + lane];
+            }
+            if (h == 0) A.part[(long long)((int)blockIdx.x - c_first) * A.out_ld + row] = acc;
+            __threadfence();
+            named_bar_sync(1, kEpiThreads);
+            if (ew == 0 && lane == 0) {
+                const unsigned int ticket = atomicAdd(&A.counters[blk], 1u);
+                is_last = ticket == (unsigned int)(c_last - c_first);
+            }
+            named_bar_sync(1, kEpiThreads);
+            if (is_last) {
+                __threadfence();
+                double vmax = 0.0;
+                if (h == 0) {
+                    if (row < A.out_n) {
+                        double sum = 0.0;
+                        for (int sl = 0; sl <= c_last - c_first; ++sl) sum += __ldcg(A.part + (long long)sl * A.out_ld + row);
+                        sum *= exp2(A.resid[row]);
+                        vmax = online_apply<COLPASS>(mode, (int)row, sum, V, ctrl, rowsum_out);
+                    }
+                    if (mode == 0) {
+                        vmax = warp_max(vmax);
+                        if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+                    }
+                }
+                __threadfence();
+                named_bar_sync(1, kEpiThreads);
+                if (ew == 0 && lane == 0) {
+                    A.counters[blk] = 0;
+                    if (mode == 0 && COLPASS) {
+                        const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
+                        if (ticket == (unsigned int)(A.n_blocks - 1)) {
+                            __threadfence();
+                            ctrl->col_tiles_done = 0;
+                            close_iteration(ctrl);
+                        }
+                    }
+                }
+            }
+            TC_T1(c_fin);
         }
-        A.part[(long long)blockIdx.y * A.out_ld + o0 + wg * kTcM + q * 32 + lane] = acc;
         if (prof && lane == 0) {
-            long long *dst = A.prof + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + ew) * 4;
-            dst[0] = clock64() - c_t0, dst[1] = c_acc, dst[2] = c_ld, dst[3] = n_tiles;
+            long long *dst = A.prof + ((long long)blockIdx.x * (RB * EW) + ew) * 8;
+            dst[0] = clock64() - c_t0, dst[1] = c_acc, dst[2] = c_ld, dst[3] = (long long)n_units;
+            dst[4] = c_pro, dst[5] = c_fin;
         }
 #undef TC_T0
 #undef TC_T1
     }
     tc_fence_before();
-    __threadfence();
     __syncthreads();
     if (wid == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcTmemCols)
                      : "memory");
-    }
-    if (tid == 0) {
-        const unsigned int ticket = atomicAdd(&A.counters[out_blk], 1u);
-        is_last = ticket == gridDim.y - 1;
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // ---- last CTA of this out block: sum the segments in order and apply the update -----------------
-    double vmax = 0.0;
-    if (wid >= kTcEpiWarp0) {
-        const long long o = o0 + (tid - kTcEpiWarp0 * 32);
-        if (o < A.out_n) {
-            double s = 0.0;
-            for (int sg = 0; sg < A.nseg; ++sg) s += __ldcg(A.part + (long long)sg * A.out_ld + o);
-            s *= exp2(A.resid[o]);
-            vmax = online_apply<COLPASS>(mode, (int)o, s, V, ctrl, rowsum_out);
-        }
-        if (mode == 0) {
-            vmax = warp_max(vmax);
-            if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
-        }
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        A.counters[out_blk] = 0;
-        if (mode == 0 && COLPASS) {
-            const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
-            if (ticket == gridDim.x - 1) {
-                __threadfence();
-                ctrl->col_tiles_done = 0;
-                close_iteration(ctrl);
-            }
-        }
     }
 }
 
@@ -489,15 +539,17 @@ inline int tc_kseg(int d) { return (int)round_up(d + 2, 16); }
 inline bool tc_supported(int d) { return tc_kseg(d) <= kTcMaxKseg; }
 
 struct TcPlan {
-    int kseg = 0, n_stages = 0;
+    int kseg = 0, n_stages = 0, ew = 4;
     size_t smem = 0;
+    int threads() const { return 128 + kTcRowBlocks * ew * 32; }
 };
 
-inline TcPlan tc_plan(int d) {
+inline TcPlan tc_plan(int d, int ew = 4) {
     TcPlan p;
     p.kseg = tc_kseg(d);
+    p.ew = ew;
     const size_t row_bytes = (size_t)p.kseg * 6;
-    const size_t a = (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes;
+    const size_t a = 2 * (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes;  // A double buffered
     int s = (int)((kTcSmemLimit - a - kTcTail) / b);
     if (s > kTcMaxStages) s = kTcMaxStages;
     p.n_stages = s;
@@ -505,56 +557,52 @@ inline TcPlan tc_plan(int d) {
     return p;
 }
 
-// Segments of the in side: minimise (waves of CTAs) x (tiles per CTA + fixed per-CTA cost).
-inline int tc_segments(int sm_count, int out_blocks, int in_tiles, int *seg_tiles) {
-    if (out_blocks < 1) out_blocks = 1;
-    if (in_tiles < 1) in_tiles = 1;
-    int best = 1;
-    double best_cost = 1e300;
-    for (int s = 1; s <= in_tiles && s <= 64; ++s) {
-        const int per = (int)cdiv(in_tiles, s);
-        const int real = (int)cdiv(in_tiles, per);
-        if (real != s) continue;
-        const int64_t waves = cdiv((int64_t)out_blocks * s, sm_count);
-        const double cost = (double)waves * (per + 4.0);
-        if (cost < best_cost - 1e-9) {
-            best_cost = cost;
-            best = s;
-        }
-    }
-    *seg_tiles = (int)cdiv(in_tiles, best);
-    return best;
+// One-wave grid and the number of partial-sum slots an out block can receive.
+inline int tc_grid(int sm_count, int n_blocks, int in_tiles, int *max_slots) {
+    const long long T = (long long)n_blocks * in_tiles;
+    const int G = (int)(T < sm_count ? T : sm_count);
+    *max_slots = (int)cdiv(G, n_blocks) + 1;
+    return G;
 }
 
-template <int KSEG>
+template <int KSEG, int EW>
 inline int tc_configure_one(int bytes) {
-    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<false, KSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<true, KSEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<false, KSEG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<true, KSEG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     return WOTB_OK;
 }
 
 inline int tc_configure(const TcPlan &plan) {
-    static size_t configured[3] = {0, 0, 0};
-    const int k = plan.kseg / 16 - 1;
-    if (configured[k] < plan.smem) {
+    static size_t configured[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    const int k = plan.kseg / 16 - 1, e = plan.ew == 8;
+    if (configured[k][e] < plan.smem) {
         const int bytes = (int)plan.smem;
-        if (plan.kseg == 16) WOTB_TRY(tc_configure_one<16>(bytes));
-        if (plan.kseg == 32) WOTB_TRY(tc_configure_one<32>(bytes));
-        if (plan.kseg == 48) WOTB_TRY(tc_configure_one<48>(bytes));
-        configured[k] = plan.smem;
+        if (plan.kseg == 16 && !e) WOTB_TRY((tc_configure_one<16, 4>(bytes)));
+        if (plan.kseg == 32 && !e) WOTB_TRY((tc_configure_one<32, 4>(bytes)));
+        if (plan.kseg == 48 && !e) WOTB_TRY((tc_configure_one<48, 4>(bytes)));
+        if (plan.kseg == 16 && e) WOTB_TRY((tc_configure_one<16, 8>(bytes)));
+        if (plan.kseg == 32 && e) WOTB_TRY((tc_configure_one<32, 8>(bytes)));
+        if (plan.kseg == 48 && e) WOTB_TRY((tc_configure_one<48, 8>(bytes)));
+        configured[k][e] = plan.smem;
     }
     return WOTB_OK;
 }
 
 template <bool COLPASS>
-inline void tc_launch(const TcPlan &plan, dim3 grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
+inline void tc_launch(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
                       int mode, double *rowsum_out) {
-    if (plan.kseg == 16)
-        k_online_tc<COLPASS, 16><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
-    else if (plan.kseg == 32)
-        k_online_tc<COLPASS, 32><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
-    else
-        k_online_tc<COLPASS, 48><<<grid, kTcThreads, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out);
+#define WOTB_TC_CASE(K, E)                                                                                        \
+    if (plan.kseg == K && plan.ew == E) {                                                                         \
+        k_online_tc<COLPASS, K, E><<<grid, 128 + kTcRowBlocks * E * 32, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out); \
+        return;                                                                                                   \
+    }
+    WOTB_TC_CASE(16, 4)
+    WOTB_TC_CASE(32, 4)
+    WOTB_TC_CASE(48, 4)
+    WOTB_TC_CASE(16, 8)
+    WOTB_TC_CASE(32, 8)
+    WOTB_TC_CASE(48, 8)
+#undef WOTB_TC_CASE
 }
 
 }  // namespace wotb
@@ -574,7 +622,8 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     WOTB_REQUIRE(n_out >= 1 && n_in >= 1 && d >= 1 && reps >= 1, "bad sizes");
     const int dbg = impl >> 4;
     impl &= 15;
-    WOTB_REQUIRE(impl == 0 || (impl == 1 && tc_supported(d)), "impl: 0 SIMT FP32, 1 tcgen05 (d <= 46)");
+    WOTB_REQUIRE(impl == 0 || ((impl == 1 || impl == 2) && tc_supported(d)),
+                 "impl: 0 SIMT FP32, 1 tcgen05 with 8 epilogue warps, 2 tcgen05 with 16 (d <= 46)");
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     wotb_params prm;
@@ -598,15 +647,15 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     };
     float ms = 0.f;
     if (impl >= 1) {
-        const TcPlan plan = tc_plan(d);
+        const TcPlan plan = tc_plan(d, impl == 2 ? 8 : 4);
         WOTB_TRY(tc_configure(plan));
         const int64_t po = round_up(n_out, kTcOut), pi = round_up(n_in, kTcOut);
         const size_t row_bytes = (size_t)plan.kseg * 6;
         const int out_blocks = (int)cdiv(n_out, kTcOut), in_tiles = (int)cdiv(n_in, kTcN);
-        int seg_tiles = 0;
-        const int nseg = tc_segments(ctx->sm_count, out_blocks, in_tiles, &seg_tiles);
+        int max_slots = 0;
+        const int grid = tc_grid(ctx->sm_count, out_blocks, in_tiles, &max_slots);
         const size_t o_ao = take(po * row_bytes), o_bo = take(po * row_bytes), o_ai = take(pi * row_bytes),
-                     o_bi = take(pi * row_bytes), o_res = take(po * 8), o_part = take((size_t)nseg * po * 8),
+                     o_bi = take(pi * row_bytes), o_res = take(po * 8), o_part = take((size_t)max_slots * po * 8),
                      o_cnt = take((size_t)out_blocks * 4 + 64);
         WOTB_TRY(ctx->onl.reserve(off));
         char *ob = ctx->onl.as<char>();
@@ -618,18 +667,17 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         k_tc_pack<<<(unsigned)cdiv(po * cpr, 256), 256, 0, st>>>(x_out, (int)n_out, d, po, plan.kseg, Ao, Bo, nullptr, scale);
         k_tc_pack<<<(unsigned)cdiv(pi * cpr, 256), 256, 0, st>>>(x_in, (int)n_in, d, pi, plan.kseg, Ai, Bi, nullptr, scale);
         k_tc_slots<<<(unsigned)cdiv(n_out > n_in ? n_out : n_in, 256), 256, 0, st>>>(off_out, (int)n_out, Ao, resid, off_in,
-                                                                                     (int)n_in, Bi, plan.kseg, nullptr);
+                                                                                     (int)n_in, Bi, plan.kseg, nullptr, 0);
         TcArgs A;
-        A.opA = Ao, A.opB = Bi, A.resid = resid, A.out_n = (int)n_out, A.out_ld = po, A.kseg = plan.kseg;
-        A.n_stages = plan.n_stages, A.nseg = nseg, A.seg_tiles = seg_tiles, A.part = part, A.counters = cnt;
-        A.out_blk0 = 0, A.in_tile0 = 0, A.in_ntiles = in_tiles, A.dbg = dbg;
+        A.opA = Ao, A.opB = Bi, A.resid = resid, A.out_n = (int)n_out, A.out_ld = po;
+        A.n_blocks = out_blocks, A.out_blk0 = 0, A.in_tile0 = 0, A.in_ntiles = in_tiles;
+        A.n_stages = plan.n_stages, A.part = part, A.counters = cnt, A.dbg = dbg;
         A.prof = nullptr;
-        const size_t prof_n = (size_t)out_blocks * nseg * 8 * 4;
         if (dbg & 8) {
-            WOTB_TRY(ctx->hTmp.reserve(prof_n * 8));
+            WOTB_TRY(ctx->hTmp.reserve((size_t)ctx->sm_count * 16 * 8 * 8));
+            WOTB_CUDA(cudaMemsetAsync(ctx->hTmp.ptr, 0, (size_t)ctx->sm_count * 16 * 8 * 8, st));
             A.prof = ctx->hTmp.as<long long>();
         }
-        const dim3 grid(out_blocks, nseg);
         tc_launch<false>(plan, grid, st, A, V, d_ctrl, 4, sums);
         WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
         for (int r = 0; r < reps; ++r) tc_launch<false>(plan, grid, st, A, V, d_ctrl, 4, sums);
@@ -672,19 +720,24 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     WOTB_CUDA(cudaGetLastError());
     WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_pass) *ms_per_pass = ms / reps;
-    if (impl == 1 && (dbg & 8)) {  // cycle counters of the last launch: mean over the epilogue warps
-        const size_t n = ctx->hTmp.cap / 8 < 8 * 4 * 65536 ? ctx->hTmp.cap / 8 : 8 * 4 * 65536;
+    if (impl >= 1 && (dbg & 8)) {  // cycle counters of the last launch: mean over the epilogue warps
+        const size_t n = (size_t)ctx->sm_count * 16 * 8;
         std::vector<long long> hp(n);
         WOTB_CUDA(cudaMemcpy(hp.data(), ctx->hTmp.ptr, n * 8, cudaMemcpyDeviceToHost));
-        double tot = 0, wa = 0, wl = 0, tiles = 0;
+        double tot = 0, wa = 0, wl = 0, tiles = 0, pro = 0, fin = 0, tmax = 0;
         size_t warps = 0;
-        for (size_t w = 0; w + 3 < n; w += 4) {
-            if (hp[w + 3] <= 0 || hp[w + 3] > 100000) continue;
-            tot += hp[w], wa += hp[w + 1], wl += hp[w + 2], tiles += hp[w + 3];
+        for (size_t w = 0; w + 7 < n; w += 8) {
+            if (hp[w + 3] <= 0) continue;
+            tot += hp[w], wa += hp[w + 1], wl += hp[w + 2], tiles += hp[w + 3], pro += hp[w + 4], fin += hp[w + 5];
+            if ((double)hp[w] > tmax) tmax = (double)hp[w];
             ++warps;
         }
-        if (warps) fprintf(stderr, "[tc prof] warps %zu tiles/warp %.1f | cycles per tile: total %.0f, waiting for accumulators %.0f, waiting for tcgen05.ld %.0f\n",
-                           warps, tiles / warps, tot / tiles, wa / tiles, wl / tiles);
+        if (warps)
+            fprintf(stderr,
+                    "[tc prof] warps %zu units/warp %.1f | cycles per warp: total %.0f (max %.0f) = prologue %.0f + publish/finish "
+                    "%.0f + loop; per unit in loop %.0f, of which waiting for accumulators %.0f, for tcgen05.ld %.0f\n",
+                    warps, tiles / warps, tot / warps, tmax, pro / warps, fin / warps, (tot - pro - fin) / tiles, wa / tiles,
+                    wl / tiles);
     }
     return WOTB_OK;
 }

@@ -767,6 +767,8 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.nx = V.ny = nullptr;
     V.Ps = V.Qs = V.Pd = V.Qd = nullptr;
     V.n_pad_i = V.n_pad_j = 0;
+    V.tcXB = V.tcYB = nullptr;
+    V.tc_kseg = 0;
     WOTB_CUDA(cudaMemsetAsync(V.tile_counters, 0, (size_t)n_col_tiles * 4 + 64, ctx->stream));
     WOTB_CUDA(cudaMemsetAsync(V.sumK0_part, 0, (size_t)n_k0_part * 8 + 64, ctx->stream));
     *out = V;
@@ -1105,8 +1107,7 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
 
 }  // namespace wotb
 
-#include "online_pass.cuh"
-#include "online_tc.cuh"
+#include "online_solve.cuh"
 
 namespace wotb {
 int sinkhorn_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
@@ -1114,8 +1115,8 @@ int sinkhorn_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1
     return sinkhorn_online_impl(ctx, x0, I, x1, J, d, median, G, prm, f, g, rowsum, info);
 }
 void online_rows(OnlineSolve *S, int64_t *lo, int64_t *hi) {
-    *lo = S->row_lo;
-    *hi = S->row_hi;
+    *lo = S->P.row_lo;
+    *hi = S->P.row_hi;
 }
 void online_close(OnlineSolve *S) { delete S; }
 }  // namespace wotb

@@ -8,6 +8,8 @@
 // machine.  No host synchronisation sits between iterations, batches or epsilon stages.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 struct SolveCtrl {
@@ -80,4 +82,7 @@ struct SolveVecs {
     double *Ps, *Qs;         // c1 u_i - c2 |x_i|^2 and c1 v_j - c2 |y_j|^2   (change on absorption / new eps)
     double *Pd, *Qd;         // Ps + log2(a_i / I) and Qs + log2(b_j / J)      (change every half-step)
     long long n_pad_i, n_pad_j;  // padded lengths; padding holds -inf so padded entries add exp2(-inf) = 0
+    // ---- tcgen05 online kernel only: the B-role operand rows whose offset slots follow Pd / Qd (online_tc.cuh) ----
+    __half *tcXB, *tcYB;
+    int tc_kseg;
 };

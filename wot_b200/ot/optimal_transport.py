@@ -28,11 +28,15 @@ def last_solve_info():
 
 
 def _kernel_id(kernel):
+    """(wotb_kernel, force_simt).  'online' uses the tcgen05 pass kernel when d <= 46 and the SIMT FP32 kernel
+    otherwise; 'online_simt' forces the latter."""
     if kernel in (None, "stored", _lib.KERNEL_STORED):
-        return _lib.KERNEL_STORED
+        return _lib.KERNEL_STORED, False
     if kernel in ("online", _lib.KERNEL_ONLINE):
-        return _lib.KERNEL_ONLINE
-    raise ValueError("kernel must be 'stored' or 'online'")
+        return _lib.KERNEL_ONLINE, False
+    if kernel == "online_simt":
+        return _lib.KERNEL_ONLINE, True
+    raise ValueError("kernel must be 'stored', 'online' or 'online_simt'")
 
 
 def _out_array(shape, out, out_dtype, pinned):
@@ -96,7 +100,8 @@ def solve_coords(x0, x1, G, solver_id, scale=None, growth_iters=1, kernel="store
         if scale.shape != (d,):
             raise ValueError("scale must have one entry per coordinate")
     growth_iters = int(growth_iters)
-    prm = _lib.make_params(solver=solver_id, kernel=_kernel_id(kernel), **params)
+    kernel_id, simt = _kernel_id(kernel)
+    prm = _lib.make_params(solver=solver_id, kernel=kernel_id, online_simt=simt, **params)
     ctx = _lib.context(device)
     tmap = _out_array((n_i, n_j), out, out_dtype, pinned) if want_tmap else None
     learned = np.empty((growth_iters + 1, n_i))
