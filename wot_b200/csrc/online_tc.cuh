@@ -203,6 +203,25 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
                  :                                                                                                    \
                  : "memory")
 
+// exp2 on the FMA pipe: round-to-nearest split x = n + r (magic-number add), degree-5 minimax polynomial for 2^r on
+// [-0.5, 0.5] (max relative error 2.4e-7 in fp32 Horner form, the same as MUFU.EX2), 2^n inserted into the exponent
+// field with one integer multiply-add.  The MUFU pipe (16 ex2 per clock and SM) is the roof of this kernel while
+// the FMA pipes idle, so a quarter of every 32-column chunk is evaluated this way (the FlashAttention-4 trick).
+__device__ __forceinline__ float exp2_fma(float x) {
+    x = fminf(fmaxf(x, -126.f), 126.f);
+    const float t = x + 12582912.f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float r = x - (t - 12582912.f);
+    float p = 0.0013276470126584172f;
+    p = fmaf(p, r, 0.009675540961325169f);
+    p = fmaf(p, r, 0.05550713464617729f);
+    p = fmaf(p, r, 0.24022120237350464f);
+    p = fmaf(p, r, 0.6931469440460205f);
+    p = fmaf(p, r, 1.0000001192092896f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+constexpr int kTcFmaEvery = 4;  // one of every kTcFmaEvery entries goes to the FMA pipe (0: none)
+
 __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -210,7 +229,7 @@ __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
         s0 += ex2_approx(__uint_as_float(v[e]));
         s1 += ex2_approx(__uint_as_float(v[e + 1]));
         s2 += ex2_approx(__uint_as_float(v[e + 2]));
-        s3 += ex2_approx(__uint_as_float(v[e + 3]));
+        s3 += (kTcFmaEvery == 4) ? exp2_fma(__uint_as_float(v[e + 3])) : ex2_approx(__uint_as_float(v[e + 3]));
     }
     return (s0 + s1) + (s2 + s3);
 }
@@ -293,7 +312,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], RB);  // one commit per MMA warp
         }
         for (int b = 0; b < 2 * RB; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&a_full[b], 1);
-            mbar_init(&a_empty[b], 1);
+            mbar_init(&a_empty[b], RB);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -344,50 +363,55 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                 g += n_in_seg;
             }
         }
-    } else if (wid == 1) {
-        // ===== MMA issuer: the whole warp runs the loop (uniform control flow and descriptors), one elected
-        // lane issues.  Issue-side cost matters: with per-lane descriptor arithmetic the issuing thread, not
-        // the tensor pipe, bounded the pass (~100 clocks per instruction, measured) =====
+    } else if (wid <= RB) {
+        // ===== MMA issuers: warp 1 + rb feeds the accumulators of row block rb.  The whole warp runs the loop (uniform
+        // control flow and descriptors), one elected lane issues.  Measured: the issuing warp, not the tensor pipe, is
+        // what can bound this kernel -- an MMA costs ~48 clocks back to back, but a barrier wait ~150-250 and a commit
+        // ~200, and with per-lane descriptor arithmetic ~100 per instruction -- hence one issuing warp per row block,
+        // so that each spends one accumulator wait, six MMAs and two commits per 256 x 128 unit =====
         // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N, M
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
         const bool skip_mma = (A.dbg & 1) != 0;
         constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * 48u;  // 3*kseg/8 chunks of 16 B per row, 128 B per 8 rows
         constexpr int ksteps = 3 * kseg / 16;                       // K = 16 halves = two chunks per instruction
+        const int rb = wid - 1;
         const uint64_t descA0 = umma_desc(smem_u32(sA), lbo, sbo);
         const uint64_t descB0 = umma_desc(smem_u32(sB), lbo, sbo);
         int s = 0, seg = 0, t = t_first;
         uint32_t full_par = 0, u = 0;
+        const bool mprof = (A.dbg & 8) != 0;
+        long long m_t0 = clock64(), m_full = 0, m_acc = 0, m_issue = 0, m_x = 0;
+#define TC_M0() if (mprof) m_x = clock64()
+#define TC_M1(dst) if (mprof) dst += clock64() - m_x
         for (long long g = g0; g < g1; ++seg, t = 0) {
             const int abuf = seg & 1;
             mbar_wait_warp(&a_full[abuf], (uint32_t)((seg >> 1) & 1));
             const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+            const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
             for (int k = 0; k < n_in_seg; ++k, ++u) {
                 const uint32_t buf = u & 1u, par = (u >> 1) & 1u;
+                TC_M0();
+                mbar_wait_warp(&acc_empty[buf * RB + rb], par ^ 1u);
+                TC_M1(m_acc);
+                TC_M0();
                 mbar_wait_warp(&full[s], full_par);
+                TC_M1(m_full);
+                tc_fence_after();
+                TC_M0();
                 const uint64_t descB = descB0 + (uint64_t)(((uint32_t)s * b_bytes) >> 4);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcAccCols + rb * NT);
+                if (elect_one()) {
+                    if (!skip_mma) {
 #pragma unroll
-                for (int rb = 0; rb < RB; ++rb) {
-                    // the two row blocks are committed separately: the warps of row block 1 run half a tile behind
-                    // those of row block 0, so the epilogue warps of a scheduler do not sit at a tile boundary together
-                    mbar_wait_warp(&acc_empty[buf * RB + rb], par ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcAccCols + rb * NT);
-                    const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
-                    if (elect_one()) {
-                        if (!skip_mma) {
-#pragma unroll
-                            for (int j = 0; j < ksteps; ++j)
-                                umma_f16(d_tmem, descA + (uint64_t)(j * 16), descB + (uint64_t)(j * 16), idesc,
-                                         j > 0 ? 1u : 0u);
-                        }
-                        umma_commit(&acc_full[buf * RB + rb]);
-                        if (rb == RB - 1) {
-                            umma_commit(&empty[s]);                             // the stage is free once these MMAs have read it
-                            if (k == n_in_seg - 1) umma_commit(&a_empty[abuf]);  // and so are the A blocks of this segment
-                        }
+                        for (int j = 0; j < ksteps; ++j)
+                            umma_f16(d_tmem, descA + (uint64_t)(j * 16), descB + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
                     }
-                    __syncwarp();
+                    umma_commit(&acc_full[buf * RB + rb]);
+                    umma_commit(&empty[s]);                              // the stage is free once both warps' MMAs have read it
+                    if (k == n_in_seg - 1) umma_commit(&a_empty[abuf]);  // and so are the A blocks of this segment
                 }
+                __syncwarp();
+                TC_M1(m_issue);
                 if (++s == S) {
                     s = 0;
                     full_par ^= 1u;
@@ -395,6 +419,12 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             }
             g += n_in_seg;
         }
+        if (mprof && lane == 0 && rb == 0) {
+            long long *dst = A.prof + ((long long)gridDim.x * 16 + blockIdx.x) * 8;
+            dst[0] = clock64() - m_t0, dst[1] = m_full, dst[2] = m_acc, dst[3] = m_issue, dst[4] = (long long)u;
+        }
+#undef TC_M0
+#undef TC_M1
     } else if (wid >= kTcEpiWarp0) {
         // ===== epilogue: thread = one out row x (128 / (EW / 4)) columns of every tile; exp2 + in-thread sum =====
         const int ew = wid - kTcEpiWarp0;
@@ -646,6 +676,7 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         return at;
     };
     float ms = 0.f;
+    int grid_used = 0;
     if (impl >= 1) {
         const TcPlan plan = tc_plan(d, impl == 2 ? 8 : 4);
         WOTB_TRY(tc_configure(plan));
@@ -654,6 +685,7 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         const int out_blocks = (int)cdiv(n_out, kTcOut), in_tiles = (int)cdiv(n_in, kTcN);
         int max_slots = 0;
         const int grid = tc_grid(ctx->sm_count, out_blocks, in_tiles, &max_slots);
+        grid_used = grid;
         const size_t o_ao = take(po * row_bytes), o_bo = take(po * row_bytes), o_ai = take(pi * row_bytes),
                      o_bi = take(pi * row_bytes), o_res = take(po * 8), o_part = take((size_t)max_slots * po * 8),
                      o_cnt = take((size_t)out_blocks * 4 + 64);
@@ -674,8 +706,8 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         A.n_stages = plan.n_stages, A.part = part, A.counters = cnt, A.dbg = dbg;
         A.prof = nullptr;
         if (dbg & 8) {
-            WOTB_TRY(ctx->hTmp.reserve((size_t)ctx->sm_count * 16 * 8 * 8));
-            WOTB_CUDA(cudaMemsetAsync(ctx->hTmp.ptr, 0, (size_t)ctx->sm_count * 16 * 8 * 8, st));
+            WOTB_TRY(ctx->hTmp.reserve((size_t)ctx->sm_count * 17 * 8 * 8));
+            WOTB_CUDA(cudaMemsetAsync(ctx->hTmp.ptr, 0, (size_t)ctx->sm_count * 17 * 8 * 8, st));
             A.prof = ctx->hTmp.as<long long>();
         }
         tc_launch<false>(plan, grid, st, A, V, d_ctrl, 4, sums);
@@ -721,9 +753,9 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     WOTB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (ms_per_pass) *ms_per_pass = ms / reps;
     if (impl >= 1 && (dbg & 8)) {  // cycle counters of the last launch: mean over the epilogue warps
-        const size_t n = (size_t)ctx->sm_count * 16 * 8;
-        std::vector<long long> hp(n);
-        WOTB_CUDA(cudaMemcpy(hp.data(), ctx->hTmp.ptr, n * 8, cudaMemcpyDeviceToHost));
+        const size_t n = (size_t)grid_used * 16 * 8, nm = (size_t)grid_used * 8;
+        std::vector<long long> hp(n + nm);
+        WOTB_CUDA(cudaMemcpy(hp.data(), ctx->hTmp.ptr, (n + nm) * 8, cudaMemcpyDeviceToHost));
         double tot = 0, wa = 0, wl = 0, tiles = 0, pro = 0, fin = 0, tmax = 0;
         size_t warps = 0;
         for (size_t w = 0; w + 7 < n; w += 8) {
@@ -738,6 +770,11 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
                     "%.0f + loop; per unit in loop %.0f, of which waiting for accumulators %.0f, for tcgen05.ld %.0f\n",
                     warps, tiles / warps, tot / warps, tmax, pro / warps, fin / warps, (tot - pro - fin) / tiles, wa / tiles,
                     wl / tiles);
+        double mt = 0, mf = 0, ma = 0, mi = 0, mu = 0;
+        for (size_t c = 0; c < nm; c += 8) mt += hp[n + c], mf += hp[n + c + 1], ma += hp[n + c + 2], mi += hp[n + c + 3], mu += hp[n + c + 4];
+        if (mu > 0)
+            fprintf(stderr, "[tc prof] MMA warp, cycles per unit: total %.0f = waiting for B tiles %.0f + waiting for free accumulators %.0f + "
+                            "issue and commit %.0f + rest\n", mt / mu, mf / mu, ma / mu, mi / mu);
     }
     return WOTB_OK;
 }
