@@ -13,7 +13,14 @@ per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.
          stream, max over ranks.
   e2e    the same through the host-buffer C-ABI call (wotb_transport_map_from_coords_host): coordinates
          copied from pinned host memory, the float64 coupling, growth rows and potentials copied back.
-  roofline  stored-K matvec kernels (k_row / k_col), HBM-bound: algorithmic bytes = I*ld*4 per launch.
+  roofline  the dominant kernel of the selected variant, measured live on the mean atlas shape:
+            --kernel online (default): k_online_tc, one half-iteration pass that recomputes exp2 of all I*J
+            entries from coordinates on tcgen05 + MUFU; bound = MUFU.EX2 throughput (BASELINE.json names the
+            MUFU roofline for this variant), algorithmic work = I*J exp evaluations per launch, peak = the
+            MUFU.EX2 rate measured on this GPU (wotb_bench_mufu_dev; MEASURED_PEAKS.json has no MUFU figure).
+            --kernel stored: k_fused, one Sinkhorn iteration streaming K once; bound = HBM, algorithmic bytes
+            = 4*I*ld per launch, peak = MEASURED_PEAKS.json hbm_gbs.  The other variant's figures ride along
+            as roofline_stored / roofline_online.
   cpu_baseline  the float64 NumPy port of the reference (oracle/) on a bounded sample, host cores.
 
 `--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the GPU
@@ -46,7 +53,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every day by this factor (debugging)")
-    ap.add_argument("--kernel", default="stored", choices=["stored", "online", "online_simt"])
+    ap.add_argument("--kernel", default="online", choices=["stored", "online", "online_simt"])
     ap.add_argument("--cpu-cells", type=int, default=2200, help="cells/day of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -243,6 +250,37 @@ def isolated_matvec(ctx, torch, I, J, reps=20):
     return ms_row.value, ms_col.value, ms_fused.value
 
 
+def online_pass_roofline(ctx, torch, I, J, reps=20):
+    """One k_online_tc launch (a half-iteration: exp2 of all I*J entries recomputed from coordinates, row sums
+    reduced) on a Sinkhorn-like state, timed with CUDA events on the library's stream inside
+    wotb_online_rowsums_dev; the MUFU.EX2 peak is measured on the same GPU by wotb_bench_mufu_dev."""
+    from tools.online_pass_check import make_inputs
+    from wot_b200 import _lib
+    x0, x1, scale, off_out, off_in = make_inputs(I, J, D, seed=6)
+    dev = "cuda:%d" % ctx.device
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (x0, x1, off_out, off_in)]
+    sums = torch.empty(I, dtype=torch.float64, device=dev)
+    ms, peak = C.c_double(), C.c_double()
+    P = lambda v: C.c_void_p(v.data_ptr())  # noqa: E731
+    _lib.check(ctx.lib.wotb_online_rowsums_dev(ctx.handle, P(t[0]), I, P(t[1]), J, D, float(scale), P(t[2]), P(t[3]),
+                                               2, reps, P(sums), C.byref(ms)))
+    _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak)))
+    achieved = I * J / (ms.value * 1e-3) / 1e12
+    return {
+        "bound": "mufu", "achieved": achieved, "peak": peak.value / 1e12, "unit": "Texp/s",
+        "frac": achieved / (peak.value / 1e12),
+        "traffic": 4940544, "traffic_source": "ncu --set full, profiles/r1e_k_online_tc_ncu_full.txt: dram bytes per launch "
+                                              "at 12486x12405 (operands only; nothing of size I*J exists)",
+        "peak_source": "MUFU.EX2 rate measured on this GPU (wotb_bench_mufu_dev: 16 independent ex2 chains per thread, "
+                       "32 warps per SM); nominal 16/clk/SM x 148 x 1.965 GHz = 4.65 T/s",
+        "kernel": "k_online_tc (tcgen05 cross term + offsets in TMEM, exp2 split between MUFU.EX2 and packed FMA-pipe "
+                  "polynomial, one half-iteration per launch)",
+        "shape": [I, J], "algorithmic_exp_per_launch": I * J, "pass_ms": ms.value,
+        "note": "achieved counts exponentials evaluated per second; entries moved to the FMA pipe make fractions above "
+                "1.0 possible in principle",
+    }
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from wot_b200 import _lib, _pinned, synthetic
@@ -302,6 +340,7 @@ def run_ours(args, rank, world, local_rank):
     iters = launches = 0
     mv_bytes = mv_launch = 0
     solve_ms = 0.0
+    entry_iters = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for s in range(args.warmup, total):
         dp.load(*coords[mine[s]])           # synthetic coordinates placed in HBM outside the timed region
@@ -314,6 +353,7 @@ def run_ours(args, rank, world, local_rank):
             iters += inf["iters"]
             launches += inf["launches"]
             solve_ms += inf["gpu_ms"]
+            entry_iters += float(inf["iters"]) * dp.I * dp.J
             b, n = matvec_bytes(inf, dp.I, dp.J, dp.J <= 23040)
             mv_bytes += b
             mv_launch += n
@@ -382,15 +422,27 @@ def run_ours(args, rank, world, local_rank):
     else:
         achieved = 2 * alg / ((ms_row + ms_col) * 1e-3) / 1e9
         kernel = "k_row + k_col (stored-K matvec pair = one Sinkhorn iteration)"
-    roofline = {
+    roofline_stored = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "kernel": kernel,
+        "traffic": 615000000, "traffic_source": "ncu --set full, profiles/r1b_k_fused_ncu_full.txt: 3.075 GB read per "
+                                                "5-iteration launch at this shape",
+        "peak_source": peak_src, "kernel": kernel,
         "shape": [ri, rj], "algorithmic_bytes_per_launch": alg,
         "fused_iter_ms": ms_fused, "row_ms": ms_row, "col_ms": ms_col,
         "row_gbs": alg / (ms_row * 1e-3) / 1e9, "col_gbs": alg / (ms_col * 1e-3) / 1e9,
-        "in_solve_gbs": mv_bytes / (solve_ms * 1e-3) / 1e9,
-        "in_solve_note": "bytes of K streamed by the timed steps / total solver device time incl. K builds and checks",
     }
+    roofline_online = online_pass_roofline(ctx, torch, ri, rj)
+    if online:
+        roofline = roofline_online
+        # all-in: every Sinkhorn iteration evaluates 2*I*J exponentials; solver device time includes operand
+        # packing, the convergence checks and the final row sums
+        roofline["in_solve_frac"] = 2.0 * entry_iters / (solve_ms * 1e-3) / roofline["peak"] / 1e12
+        other = ("roofline_stored", roofline_stored)
+    else:
+        roofline = roofline_stored
+        roofline["in_solve_gbs"] = mv_bytes / (solve_ms * 1e-3) / 1e9
+        roofline["in_solve_note"] = "bytes of K streamed by the timed steps / total solver device time incl. K builds and checks"
+        other = ("roofline_online", roofline_online)
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -406,10 +458,13 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "day-pair transport maps per second", "value": value, "unit": "tmaps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 K / f64 potentials",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ("f32 exponent (fp16x3 split on tcgen05) / f64 potentials" if online
+                                                 else "f32 K / f64 potentials"),
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "solver": "duality_gap", "kernel": args.kernel, "eps": 0.05, "lambda1": 1,
-                   "lambda2": 50, "l2": "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)",
+                   "lambda2": 50, "l2": ("every pass recomputes I*J = 25M-400M entries from L2-resident operands; nothing is cached "
+                          "between steps (each step is a different day-pair)" if online else
+                          "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)"),
                    "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale},
         "sinkhorn_iters_per_s": iters_all / t_dev,
         "sinkhorn_iters": int(iters_all),
@@ -418,6 +473,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        other[0]: other[1],
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

@@ -90,3 +90,70 @@ def test_no_overwrite_skips_existing(tmp_path):
     model.solver = None   # would raise if any pair were recomputed
     model.compute_all_transport_maps(tmap_out=out, output_file_format="npz", cost_matrices=costs, overwrite=False)
     assert os.path.getmtime(out + "_0.0_1.0.npz") == stamp
+
+
+# ---- parameter sweep (BASELINE.json configs[4]): dynamic queue over ranks ---------------------------
+def _sweep_inputs():
+    from wot_b200 import parallel, synthetic
+    x0, x1, growth = synthetic.day_pair_coords(60, 70, d=5, seed=11)
+    grid = parallel.sweep_grid(epsilons=(0.05, 0.1), lambda1s=(1, 10), lambda2s=(10, 50))
+    return x0, x1, growth, grid
+
+
+def _oracle_solve(x0, x1, G, growth_iters=1, kernel=None, **params):
+    import time
+
+    from oracle import wot_oracle as orc
+    time.sleep(0.05)     # units are milliseconds long here: give the other rank time to reach the queue
+    info = orc.SolveInfo()
+    prm = dict(epsilon0=1, tau=10000, tolerance=1e-8, max_iter=1e7, batch_size=5)
+    prm.update(params)
+    tmap = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=G, info=info, **prm)
+    return {"iters": info.iters, "batches": list(info.batches), "rowsum": tmap.sum(axis=1)}
+
+
+def _sweep_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import pickle
+
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wot_b200 import parallel
+        x0, x1, growth, grid = _sweep_inputs()
+        res = parallel.parameter_sweep(x0, x1, growth, grid, solve=_oracle_solve)
+        with open(os.path.join(out_dir, "sweep_%d.pkl" % rank), "wb") as fh:
+            pickle.dump(res, fh)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sweep_grid_is_the_64_setting_grid():
+    from wot_b200 import parallel
+    grid = parallel.sweep_grid()
+    assert len(grid) == 64 and len({tuple(sorted(s.items())) for s in grid}) == 64
+    assert grid[0] == dict(epsilon=0.01, lambda1=0.1, lambda2=1.0)
+    q = parallel.WorkQueue([3, 1, 2])
+    assert list(q) == [3, 1, 2]
+
+
+@pytest.mark.timeout(300)
+def test_parameter_sweep_two_ranks_matches_serial(tmp_path):
+    import pickle
+
+    import torch.multiprocessing as mp
+
+    from wot_b200 import parallel
+    x0, x1, growth, grid = _sweep_inputs()
+    serial = parallel.parameter_sweep(x0, x1, growth, grid, solve=_oracle_solve)
+    mp.spawn(_sweep_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    per_rank = [pickle.load(open(tmp_path / ("sweep_%d.pkl" % r), "rb")) for r in range(2)]
+    ran = [0, 0]
+    for k, want in enumerate(serial):
+        assert want["setting"] == grid[k]
+        for got in (per_rank[0][k], per_rank[1][k]):     # every rank holds every result, in grid order
+            assert got["setting"] == grid[k] and got["iters"] == want["iters"] and got["batches"] == want["batches"]
+            np.testing.assert_array_equal(got["rowsum"], want["rowsum"])
+        ran[per_rank[0][k]["rank"]] += 1
+    assert sum(ran) == len(grid) and min(ran) >= 1          # both ranks drew from the queue

@@ -89,10 +89,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
+    path = os.environ.get("WOT_B200_LIB", LIB)   # developer knob: an alternative build of the same library
+    if not os.path.exists(path):
         raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                          "(wot_b200 has no CPU fallback)" % LIB)
-    lib = C.CDLL(LIB)
+                          "(wot_b200 has no CPU fallback)" % path)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -220,18 +220,84 @@ __device__ __forceinline__ float exp2_fma(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-constexpr int kTcFmaEvery = 4;  // one of every kTcFmaEvery entries goes to the FMA pipe (0: none)
+// ---- packed fp32x2 arithmetic (sm_100a: FADD2 / FFMA2 take one issue slot for two lanes of work) -----------------
+// The epilogue is bound by instruction issue together with the MUFU pipe (ncu, profiles/r1e: XU 59 %, issue 57 %,
+// 5.7 thread instructions per entry with scalar code), so everything that is not a MUFU.EX2 is done two entries at
+// a time: the running sums (FADD2) and the FMA-pipe exp2 (range reduction and Horner steps as FADD2 / FFMA2).
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float x) { return pack2(x, x); }
+
+// exp2 of two entries on the FMA pipe: the arithmetic of exp2_fma, two lanes per instruction.
+// 2 FMNMX + 3 FADD2/FFMA2 (split) + 5 FFMA2 (Horner) + 2 integer ops = 12 issue slots per pair (scalar: 26).
+__device__ __forceinline__ f32x2 exp2_fma2(float x0, float x1) {
+    x0 = fmaxf(x0, -126.f);  // padding rows carry a huge negative offset; exponents never approach +127 (the MUFU
+    x1 = fmaxf(x1, -126.f);  // entries of the same row would overflow first)
+    const f32x2 x = pack2(x0, x1);
+    const f32x2 t = fadd2(x, splat2(12582912.f));
+    const f32x2 n = fadd2(t, splat2(-12582912.f));
+    const f32x2 r = ffma2(n, splat2(-1.f), x);
+    f32x2 p = ffma2(splat2(0.0013276470126584172f), r, splat2(0.009675540961325169f));
+    p = ffma2(p, r, splat2(0.05550713464617729f));
+    p = ffma2(p, r, splat2(0.24022120237350464f));
+    p = ffma2(p, r, splat2(0.6931469440460205f));
+    p = ffma2(p, r, splat2(1.0000001192092896f));
+    float p0, p1, t0, t1;
+    unpack2(p, p0, p1);
+    unpack2(t, t0, t1);
+    return pack2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)),
+                 __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+
+// Of every 16 consecutive entries, kTcFmaPairs pairs are evaluated on the FMA pipe and the rest by MUFU.EX2 (the
+// FlashAttention-4 trick).  With packed arithmetic a pair costs 12 issue slots and a MUFU entry 1.5; the MUFU pipe
+// takes 8 clocks per warp instruction.  Measured on B200 (profiles/r1f_pairs.txt, 12486 x 12405): 0 pairs 54.9 us, 2 pairs
+// 49.3 us, 3 pairs 52.4 us, 4 pairs 55.5 us, 5 pairs 60.2 us per pass -> 2 pairs of 16 (a quarter of the entries).
+#ifndef WOTB_TC_FMA_PAIRS
+#define WOTB_TC_FMA_PAIRS 2
+#endif
+constexpr int kTcFmaPairs = WOTB_TC_FMA_PAIRS;
+
+// true when the pair (e, e + 1), e even, of a 16-entry group goes to the FMA pipe: the pairs are spread out so that
+// MUFU and FMA work interleave in program order
+__host__ __device__ constexpr bool tc_pair_on_fma(int pair) {
+    return kTcFmaPairs >= 8 ? true
+         : kTcFmaPairs <= 0 ? false
+         : ((pair + 1) * kTcFmaPairs / 8) != (pair * kTcFmaPairs / 8);
+}
 
 __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    f32x2 s0 = 0ull, s1 = 0ull;  // (0.f, 0.f)
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
-        s0 += ex2_approx(__uint_as_float(v[e]));
-        s1 += ex2_approx(__uint_as_float(v[e + 1]));
-        s2 += ex2_approx(__uint_as_float(v[e + 2]));
-        s3 += (kTcFmaEvery == 4) ? exp2_fma(__uint_as_float(v[e + 3])) : ex2_approx(__uint_as_float(v[e + 3]));
+        const float a0 = __uint_as_float(v[e]), a1 = __uint_as_float(v[e + 1]);
+        const float b0 = __uint_as_float(v[e + 2]), b1 = __uint_as_float(v[e + 3]);
+        const f32x2 ea = tc_pair_on_fma((e >> 1) & 7) ? exp2_fma2(a0, a1) : pack2(ex2_approx(a0), ex2_approx(a1));
+        const f32x2 eb = tc_pair_on_fma(((e >> 1) + 1) & 7) ? exp2_fma2(b0, b1) : pack2(ex2_approx(b0), ex2_approx(b1));
+        s0 = fadd2(s0, ea);
+        s1 = fadd2(s1, eb);
     }
-    return (s0 + s1) + (s2 + s3);
+    float lo, hi;
+    unpack2(fadd2(s0, s1), lo, hi);
+    return lo + hi;
 }
 
 struct TcArgs {

@@ -326,6 +326,56 @@ namespace wotb {
 // State machine: one CTA, O(I + J) float64 work.
 // ------------------------------------------------------------------------------------------------
 constexpr int kCheckThreads = 1024;
+// k_check runs as ONE thread-block cluster of kCheckCtas CTAs: its O(I + J) float64 log/exp work was 38 us per
+// batch on one SM (profiles/r1e: 5 % of a solve); the CTAs split every vector loop (element e belongs to the
+// same cluster thread throughout, so no cross-thread dependences arise), reductions go through distributed
+// shared memory in rank order (deterministic, identical in every CTA, so control flow stays uniform), and the
+// control block is written by thread 0 of rank 0 only.
+constexpr int kCheckCtas = 8;
+constexpr int kCheckStride = kCheckThreads * kCheckCtas;
+
+struct CheckCluster {
+    unsigned rank;
+    int tid;     // thread index within the cluster
+    bool lead;   // the one thread that writes SolveCtrl
+    double *red;   // [33] block reduction scratch
+    double *part;  // [2][8] this CTA's partial sums, read by every CTA of the cluster
+    unsigned n_red;
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ double ld_dsmem(const double *local, unsigned rank) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(local), remote;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+    return v;
+}
+
+// Cluster-wide sums of N values; every thread of every CTA gets the same result (rank order).
+template <int N>
+__device__ void cluster_sum(CheckCluster &cc, double (&x)[N]) {
+    static_assert(N <= 8, "at most 8 sums per reduction");
+    double *mine = cc.part + (cc.n_red & 1u) * 8;
+    cc.n_red += 1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double v = block_sum<kCheckThreads>(x[k], cc.red);
+        if (threadIdx.x == 0) mine[k] = v;
+    }
+    cluster_sync_all();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        double tot = 0.0;
+        for (unsigned r = 0; r < (unsigned)kCheckCtas; ++r) tot += ld_dsmem(mine + k, r);
+        x[k] = tot;
+    }
+    // no trailing barrier: the next reduction uses the other half of `part`, and a CTA can only get two
+    // reductions ahead after every CTA has arrived at the one in between, i.e. finished reading this half
+}
 
 __device__ void set_eps(SolveCtrl *c, double eps) {
     c->eps = eps;
@@ -340,14 +390,15 @@ __device__ void set_eps(SolveCtrl *c, double eps) {
 // u += eps log a, v += eps log b, a = b = 1 (:118-119, :138-141, :212-216, :221-228) and refresh
 // everything derived from (u, v, a, b).  eps_abs is the epsilon of the absorption, eps_next the
 // epsilon the following iterations run at.
-__device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double eps_abs, double eps_next) {
+__device__ void absorb(const CheckCluster &cc, const SolveVecs &V, const SolveCtrl *c, int cur, double eps_abs,
+                       double eps_next) {
     const int I = c->I, J = c->J;
     const double i1 = 1.0 / (c->lambda1 + eps_next), i2 = 1.0 / (c->lambda2 + eps_next);
     const float dxf = (float)(1.0 / (double)I), dyf = (float)(1.0 / (double)J);
     const double c1 = 1.4426950408889634 / eps_next, c2 = c1 * c->inv_median;
     const double l2dx = -log2((double)I), l2dy = -log2((double)J);
     double *a = V.a[cur], *b = V.b[cur];
-    for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+    for (int i = cc.tid; i < I; i += kCheckStride) {
         const double u = V.u[i] + eps_abs * log(a[i]);
         V.u[i] = u;
         a[i] = 1.0;
@@ -360,7 +411,7 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
             V.z[i] = dxf;
         }
     }
-    for (int j = threadIdx.x; j < J; j += kCheckThreads) {
+    for (int j = cc.tid; j < J; j += kCheckStride) {
         const double v = V.v[j] + eps_abs * log(b[j]);
         V.v[j] = v;
         b[j] = 1.0;
@@ -375,12 +426,12 @@ __device__ void absorb(const SolveVecs &V, const SolveCtrl *c, int cur, double e
     }
 }
 
-__device__ void finish(const SolveVecs &V, SolveCtrl *c, int cur, int status) {
+// `eps` is passed in: the caller may have changed c->eps in this launch, and other CTAs must not re-read it
+__device__ void finish(const CheckCluster &cc, const SolveVecs &V, SolveCtrl *c, int cur, int status, double eps) {
     const int I = c->I, J = c->J;
-    const double eps = c->eps;
-    for (int i = threadIdx.x; i < I; i += kCheckThreads) V.f[i] = V.u[i] + eps * log(V.a[cur][i]);
-    for (int j = threadIdx.x; j < J; j += kCheckThreads) V.g[j] = V.v[j] + eps * log(V.b[cur][j]);
-    if (threadIdx.x == 0) {
+    for (int i = cc.tid; i < I; i += kCheckStride) V.f[i] = V.u[i] + eps * log(V.a[cur][i]);
+    for (int j = cc.tid; j < J; j += kCheckStride) V.g[j] = V.v[j] + eps * log(V.b[cur][j]);
+    if (cc.lead) {
         c->done = 1;
         c->status = status;
         c->eps_final = eps;
@@ -388,9 +439,10 @@ __device__ void finish(const SolveVecs &V, SolveCtrl *c, int cur, int status) {
     }
 }
 
-__device__ void publish(SolveCtrl *c, volatile int *host_done) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
+__device__ void publish(const CheckCluster &cc, SolveCtrl *c, volatile int *host_done) {
+    cluster_sync_all();  // every CTA's vector writes are ordered before the flag; no CTA exits while its shared
+                         // memory may still be read by a peer
+    if (cc.lead) {
         c->seq += 1;
         if (c->done) {
             *host_done = 1;
@@ -401,16 +453,22 @@ __device__ void publish(SolveCtrl *c, volatile int *host_done) {
 
 __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl *ctrl, volatile int *host_done) {
     __shared__ double red[33];
+    __shared__ double part[16];
+    CheckCluster cc;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cc.rank));
+    cc.tid = (int)cc.rank * kCheckThreads + (int)threadIdx.x;
+    cc.lead = cc.tid == 0;
+    cc.red = red, cc.part = part, cc.n_red = 0;
     SolveCtrl *c = ctrl;
     if (c->done) {
-        publish(c, host_done);
+        publish(cc, c, host_done);
         return;
     }
     const int I = c->I, J = c->J;
     const bool complete = c->batch_done >= c->batch_iters;
     const int stop = c->stop;
     if (!complete && stop == 0) {  // the batch continues in the next replay of the sequence
-        publish(c, host_done);
+        publish(cc, c, host_done);
         return;
     }
     const bool dg = c->solver == WOTB_SOLVER_DUALITY_GAP;
@@ -418,7 +476,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
     const bool final_dg = dg && stage == WOTB_N_STAGES - 1;
     const int cur = c->cur;
     const double eps = c->eps;
-    __syncthreads();
+    cluster_sync_all();
 
     // 0. Lazy duality gap (final stage).  primal/dual of the state at the previous batch end need the row
     //    sums K (b dy) of THAT state, which is exactly what the first iteration of the batch that followed
@@ -429,7 +487,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         const double l1 = c->lambda1, l2 = c->lambda2, qm = c->q;
         const double dx = 1.0 / (double)I, dy = 1.0 / (double)J;
         double kl1 = 0.0, kl2 = 0.0, fr = 0.0, gc = 0.0, sr = 0.0, c1 = 0.0, c2 = 0.0;
-        for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+        for (int i = cc.tid; i < I; i += kCheckStride) {
             const double r = V.as[i] * V.sfirst[i] * (double)J, p = V.p[i];
             const double f = V.fs[i];
             const double x = r * dy;
@@ -439,7 +497,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
             sr += r;
             c1 += (p * dx) * (exp(-f / l1) - 1.0);
         }
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) {
+        for (int j = cc.tid; j < J; j += kCheckStride) {
             const double cj = V.cs[j];
             const double g = V.gs[j];
             const double y = cj * dx;
@@ -448,21 +506,16 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
             c2 += (qm * dy) * (exp(-g / l2) - 1.0);
         }
         double k0 = 0.0;
-        for (int k = threadIdx.x; k < V.n_sumK0_part; k += kCheckThreads) k0 += V.sumK0_part[k];
-        kl1 = block_sum<kCheckThreads>(kl1, red);
-        kl2 = block_sum<kCheckThreads>(kl2, red);
-        fr = block_sum<kCheckThreads>(fr, red);
-        gc = block_sum<kCheckThreads>(gc, red);
-        sr = block_sum<kCheckThreads>(sr, red);
-        c1 = block_sum<kCheckThreads>(c1, red);
-        c2 = block_sum<kCheckThreads>(c2, red);
-        k0 = block_sum<kCheckThreads>(k0, red);
+        for (int k = cc.tid; k < V.n_sumK0_part; k += kCheckStride) k0 += V.sumK0_part[k];
+        double sums[8] = {kl1, kl2, fr, gc, sr, c1, c2, k0};
+        cluster_sum(cc, sums);
+        kl1 = sums[0], kl2 = sums[1], fr = sums[2], gc = sums[3], sr = sums[4], c1 = sums[5], c2 = sums[6], k0 = sums[7];
         const double ij = (double)I * (double)J;
         const double pri = l1 * kl1 + l2 * kl2 + (fr + gc - eps * sr + eps * k0) / ij;
         const double dua = -l1 * c1 - l2 * c2 - eps * (sr - k0) / ij;
         const double lazy_gap = (pri - dua) / fabs(pri);
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        cluster_sync_all();
+        if (cc.lead) {
             c->primal = pri;
             c->dual = dua;
             c->sumK0 = k0;
@@ -471,12 +524,12 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
             c->snap_valid = 0;
         }
         if (!(lazy_gap > c->tolerance)) {  // converged (or NaN, :129): return the snapshot
-            for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+            for (int i = cc.tid; i < I; i += kCheckStride) {
                 V.f[i] = V.fs[i];
                 if (V.rowsum) V.rowsum[i] = V.r[i] * dy;
             }
-            for (int j = threadIdx.x; j < J; j += kCheckThreads) V.g[j] = V.gs[j];
-            if (threadIdx.x == 0) {
+            for (int j = cc.tid; j < J; j += kCheckStride) V.g[j] = V.gs[j];
+            if (cc.lead) {
                 c->done = 1;
                 c->status = lazy_gap != lazy_gap ? WOTB_STATUS_NAN : WOTB_STATUS_CONVERGED;
                 c->eps_final = eps;
@@ -484,47 +537,47 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
                 c->iter = c->snap_iter;
                 c->rowsum_ready = V.rowsum != nullptr;
             }
-            publish(c, host_done);
+            publish(cc, c, host_done);
             return;
         }
-        __syncthreads();
+        cluster_sync_all();
     }
     // 1. column sums of R = a K b at this batch end, before any absorption (R is invariant under it; a and
     //    b are not): they go into the next snapshot
     if (final_dg && complete) {
         const double *b = V.b[cur];
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) V.cs[j] = b[j] * V.t[j] * (double)I;
+        for (int j = cc.tid; j < J; j += kCheckStride) V.cs[j] = b[j] * V.t[j] * (double)I;
     }
     // 2. stabilisation (:137-141, :211-216)
     if (stop & 1) {
-        absorb(V, c, cur, eps, eps);
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        absorb(cc, V, c, cur, eps, eps);
+        cluster_sync_all();
+        if (cc.lead) {
             c->tau_count += 1;
             c->need_build = 1;
         }
     }
     // 3. max_iter exit (:143-145)
     if (stop & 2) {
-        __syncthreads();
-        finish(V, c, cur, WOTB_STATUS_MAX_ITER);
-        publish(c, host_done);
+        cluster_sync_all();
+        finish(cc, V, c, cur, WOTB_STATUS_MAX_ITER, eps);
+        publish(cc, c, host_done);
         return;
     }
     if (!complete) {  // resume the remaining iterations of this batch after the rebuild
-        __syncthreads();
-        if (threadIdx.x == 0) c->stop = 0;
-        publish(c, host_done);
+        cluster_sync_all();
+        if (cc.lead) c->stop = 0;
+        publish(cc, c, host_done);
         return;
     }
-    __syncthreads();
+    cluster_sync_all();
 
     if (!dg) {
         // ---------------- transport_stablev2 schedule (:204-232) ------------------------------
         const int phase = c->phase;
         if (phase == 1) {
-            finish(V, c, cur, WOTB_STATUS_CONVERGED);
-            publish(c, host_done);
+            finish(cc, V, c, cur, WOTB_STATUS_CONVERGED, eps);
+            publish(cc, c, host_done);
             return;
         }
         const int since = c->since + c->batch_iters;
@@ -534,18 +587,18 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         if (adjust) {
             const int level = stage + 1;
             eps_next = (c->epsilon0 - c->epsilon) * exp(-(double)level) + c->epsilon;  // get_reg, :184-185
-            absorb(V, c, cur, eps, eps_next);
+            absorb(cc, V, c, cur, eps, eps_next);
         }
-        __syncthreads();
+        cluster_sync_all();
         const bool to_extra = sdone >= c->scaling_iter;
         if (to_extra && c->extra_iter <= 0) {
-            if (threadIdx.x == 0 && adjust) set_eps(c, eps_next);
-            __syncthreads();
-            finish(V, c, cur, WOTB_STATUS_CONVERGED);
-            publish(c, host_done);
+            if (cc.lead && adjust) set_eps(c, eps_next);
+            cluster_sync_all();
+            finish(cc, V, c, cur, WOTB_STATUS_CONVERGED, adjust ? eps_next : eps);
+            publish(cc, c, host_done);
             return;
         }
-        if (threadIdx.x == 0) {
+        if (cc.lead) {
             c->stop = 0;
             c->batch_done = 0;
             c->scaling_done = sdone;
@@ -564,7 +617,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
                 c->batch_iters = c->warm ? min(c->inner_iter_max - c->since, left) : left;
             }
         }
-        publish(c, host_done);
+        publish(cc, c, host_done);
         return;
     }
 
@@ -575,24 +628,23 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         const double *a = V.a[cur], *ap = V.a[cur ^ 1], *b = V.b[cur], *bp = V.b[cur ^ 1];
         const double inv_eps = 1.0 / eps;
         double na = 0.0, da = 0.0, nb = 0.0, db = 0.0;
-        for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+        for (int i = cc.tid; i < I; i += kCheckStride) {
             const double e = exp(V.u[i] * inv_eps);
             const double full = __dmul_rn(a[i], e);
             const double diff = __dsub_rn(full, __dmul_rn(ap[i], e));
             na += full * full;
             da += diff * diff;
         }
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) {
+        for (int j = cc.tid; j < J; j += kCheckStride) {
             const double e = exp(V.v[j] * inv_eps);
             const double full = __dmul_rn(b[j], e);
             const double diff = __dsub_rn(full, __dmul_rn(bp[j], e));
             nb += full * full;
             db += diff * diff;
         }
-        na = block_sum<kCheckThreads>(na, red);
-        da = block_sum<kCheckThreads>(da, red);
-        nb = block_sum<kCheckThreads>(nb, red);
-        db = block_sum<kCheckThreads>(db, red);
+        double sums[4] = {na, da, nb, db};
+        cluster_sum(cc, sums);
+        na = sums[0], da = sums[1], nb = sums[2], db = sums[3];
         const double ga = sqrt(da) / (1.0 + sqrt(na));
         const double gb = sqrt(db) / (1.0 + sqrt(nb));
         gap = gb > ga ? gb : ga;  // Python max(ga, gb)
@@ -600,46 +652,46 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(SolveVecs V, SolveCtrl 
         // final stage: snapshot this batch end (f and g are invariant under absorption, so taking them
         // after step 2 is the same state); its gap is evaluated by the next check (step 0)
         const double *a = V.a[cur], *b = V.b[cur];
-        for (int i = threadIdx.x; i < I; i += kCheckThreads) {
+        for (int i = cc.tid; i < I; i += kCheckStride) {
             V.fs[i] = V.u[i] + eps * log(a[i]);
             V.as[i] = a[i];
         }
-        for (int j = threadIdx.x; j < J; j += kCheckThreads) V.gs[j] = V.v[j] + eps * log(b[j]);
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        for (int j = cc.tid; j < J; j += kCheckStride) V.gs[j] = V.v[j] + eps * log(b[j]);
+        cluster_sync_all();
+        if (cc.lead) {
             c->snap_valid = 1;
             c->snap_iter = c->iter;
             c->stop = 0;
             c->batch_done = 0;
         }
-        publish(c, host_done);
+        publish(cc, c, host_done);
         return;
     }
     const double threshold = 1e-6;      // :127 (warm stages; the final stage is handled in step 0)
     const bool again = gap > threshold;  // NaN leaves the while loop, :129
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    cluster_sync_all();
+    if (cc.lead) {
         c->gap = gap;
         c->batches[stage] += 1;
         c->stop = 0;
         c->batch_done = 0;
     }
     if (again) {
-        publish(c, host_done);
+        publish(cc, c, host_done);
         return;
     }
     // next epsilon stage: absorb at the old epsilon (:118-119), then shrink (:120)
     const double eps_next = c->eps_sched[stage + 1];
-    absorb(V, c, cur, eps, eps_next);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    absorb(cc, V, c, cur, eps, eps_next);
+    cluster_sync_all();
+    if (cc.lead) {
         c->stage = stage + 1;
         set_eps(c, eps_next);
         c->need_build = 1;
         c->snap_valid = 0;
         c->batch_iters = (stage + 1 == WOTB_N_STAGES - 1) ? c->batch_size : 5;  // :130
     }
-    publish(c, host_done);
+    publish(cc, c, host_done);
 }
 
 // Vector initialisation: u = v = 0, a = b = 1, q = mean(G) (:107-111, :192-196).
@@ -860,7 +912,14 @@ void launch_init(wotb_ctx *ctx, const SolveVecs &V, SolveCtrl *d_ctrl, int64_t l
 }
 
 void launch_check(wotb_ctx *ctx, const SolveVecs &V, SolveCtrl *d_ctrl, volatile int *host_done) {
-    k_check<<<1, kCheckThreads, 0, ctx->stream>>>(V, d_ctrl, host_done);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kCheckCtas), cfg.blockDim = dim3(kCheckThreads), cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kCheckCtas, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_check, V, d_ctrl, host_done);
 }
 
 // Replays `sequence` (one batch worth of launches ending in the check kernel) until the device

@@ -3,8 +3,8 @@
 Two partitionings (BASELINE.json north_star):
 
 1. Independent day-pairs (and parameter settings) share nothing: `shard_units` deals them to ranks,
-   longest first; `compute_all_transport_maps` runs a rank's pairs and gathers the learned-growth tables so
-   the outputs (file names, `{prefix}_g.txt` row order, --no_overwrite skipping) equal the serial loop of
+   longest first (`parameter_sweep` uses a dynamic `WorkQueue` instead, iteration counts being unknown);
+   `compute_all_transport_maps` runs a rank's pairs and gathers the learned-growth tables so the outputs (file names, `{prefix}_g.txt` row order, --no_overwrite skipping) equal the serial loop of
    the reference (ot_model.py:182-201).  No collective sits on the data path.
 
 2. One very large pair is row-sharded: `sharded_online_solve` drives the stepping entry points of the
@@ -100,6 +100,98 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
     if world > 1:
         dist.barrier(group=group)
     return [day_pairs[k] for k in mine]
+
+
+def sweep_grid(epsilons=(0.01, 0.025, 0.05, 0.1), lambda1s=(0.1, 1, 10, 50), lambda2s=(1, 10, 50, 100)):
+    """The 64-setting grid of BASELINE.json configs[4] (shape of optimal_transport_validation_parameter_sweep.wdl:
+    113-146, one `wot optimal_transport_validation` task per (epsilon, lambda1, lambda2)); the reference ships no
+    parameter file, so the values are this build's.  Order: epsilon slowest."""
+    return [dict(epsilon=float(e), lambda1=float(l1), lambda2=float(l2))
+            for e in epsilons for l1 in lambda1s for l2 in lambda2s]
+
+
+class WorkQueue:
+    """Dynamic queue over the ranks of a torch.distributed job: a shared counter in the rendezvous store
+    (`store.add` is atomic), so a rank that finishes early takes the next unit.  Nothing travels on the data
+    path.  `order` is the dispatch order (longest expected unit first).  Without an initialised process group
+    it is a plain serial iterator."""
+
+    def __init__(self, order, store=None, key="wot_b200/queue"):
+        self.order, self.key = list(order), key
+        self.store = store
+        self._next = 0
+        if store is None:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    from torch.distributed.distributed_c10d import _get_default_store
+                    self.store = _get_default_store()
+            except Exception:
+                self.store = None
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        k = self.store.add(self.key, 1) - 1 if self.store is not None else self._next
+        self._next += 1
+        if k >= len(self.order):
+            raise StopIteration
+        return self.order[k]
+
+
+def expected_sweep_cost(setting):
+    """Relative cost guess used only to order the queue: iteration counts grow roughly like
+    (lambda1 + lambda2) / epsilon at fixed shape (70 .. >30k iterations)."""
+    return (setting.get("lambda1", 1.0) + setting.get("lambda2", 50.0)) / setting.get("epsilon", 0.05)
+
+
+def parameter_sweep(x0, x1, G, settings, solve=None, group=None, store=None, queue_key="wot_b200/sweep",
+                    growth_iters=1, kernel="online", **common):
+    """BASELINE.json configs[4]: many (epsilon, lambda1, lambda2) settings on ONE day-pair, settings dealt to
+    the ranks through a dynamic queue (independent units; no data-path collective).
+
+    `solve(x0, x1, G, **params) -> dict` runs one setting; the default runs the GPU growth loop from
+    coordinates without materialising the coupling and reports iteration/batch counts, the duality gap,
+    the final row sums and the potentials.  Returns, on every rank, the list of per-setting results in the
+    order of `settings` (each tagged with the rank that ran it)."""
+    rank, world = _rank_world(group)
+    if solve is None:
+        solve = _sweep_solve_gpu
+    order = sorted(range(len(settings)), key=lambda k: (-expected_sweep_cost(settings[k]), k))
+    mine = {}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier(group=group)      # start drawing together
+    for k in WorkQueue(order, store=store, key=queue_key):
+        params = dict(common)
+        params.update(settings[k])
+        res = solve(x0, x1, G, growth_iters=growth_iters, kernel=kernel, **params)
+        res["rank"] = rank
+        res["setting"] = dict(settings[k])
+        mine[k] = res
+    parts = [mine]
+    if world > 1:
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+    merged = {}
+    for part in parts:
+        merged.update(part)
+    return [merged[k] for k in range(len(settings))]
+
+
+def _sweep_solve_gpu(x0, x1, G, growth_iters=1, kernel="online", **params):
+    from . import _lib
+    from .ot import optimal_transport as wot_ot
+    device = int(os.environ.get("LOCAL_RANK", "0"))
+    _, learned = wot_ot.solve_coords(x0, x1, G, _lib.SOLVER_DUALITY_GAP, growth_iters=growth_iters, kernel=kernel,
+                                     want_tmap=False, device=device, **params)
+    last = wot_ot.last_solve_info()
+    infos = last["infos"]
+    return {"iters": sum(i["iters"] for i in infos), "batches": infos[-1]["batches"], "gap": infos[-1]["gap"],
+            "status": infos[-1]["status"], "gpu_ms": sum(i["gpu_ms"] for i in infos), "rowsum": learned[-1].copy(),
+            "f": np.array(last["f"]), "g": np.array(last["g"])}
 
 
 # ------------------------------------------------------------------------------------------------
