@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--kernel", default="online", choices=["stored", "online", "online_simt"])
     ap.add_argument("--cpu-cells", type=int, default=2200, help="cells/day of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=None,
+                    help="day-pairs in flight per GPU, each on its own CUDA stream (wot_b200.pipeline)")
     return ap.parse_args()
 
 
@@ -183,20 +185,15 @@ class DevicePair:
         self.ld_max = (max_j + 31) // 32 * 32
         self.C = torch.empty(max_i * self.ld_max if kernel == "stored" else 32, dtype=torch.float32, device=dev)
         self.out = torch.empty(max_i * max_j, dtype=torch.float64, device=dev)
-        self.x0 = torch.empty(max_i * D, dtype=torch.float64, device=dev)
-        self.x1 = torch.empty(max_j * D, dtype=torch.float64, device=dev)
         self.G = torch.empty(max_i, dtype=torch.float64, device=dev)
         self.f = torch.empty(max_i, dtype=torch.float64, device=dev)
         self.g = torch.empty(max_j, dtype=torch.float64, device=dev)
         self.rows = torch.empty(max_i, dtype=torch.float64, device=dev)
 
-    def load(self, x0, x1, growth):
-        t = self.torch
-        self.I, self.J = x0.shape[0], x1.shape[0]
-        self.x0[:x0.size].copy_(t.from_numpy(x0.ravel()))
-        self.x1[:x1.size].copy_(t.from_numpy(x1.ravel()))
-        self.G0 = t.from_numpy(growth).to(self.G.device)
-        t.cuda.synchronize()
+    def attach(self, pair, x0_dev, x1_dev, growth_dev):
+        """Point at one day-pair whose coordinates already sit in HBM."""
+        self.I, self.J = pair[0], pair[1]
+        self.x0, self.x1, self.G0 = x0_dev, x1_dev, growth_dev
 
     def run(self, prm):
         """cost + median + growth loop + coupling, inputs and outputs in HBM.  Returns per-solve infos."""
@@ -291,8 +288,13 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.Stream()
-    ctx = _lib.Context(local_rank, stream.cuda_stream)
+    from wot_b200.pipeline import Pipeline
+    # measured on B200 (profiles/r1h): two online solves in flight 7.28 tmaps/s vs 6.50 serial, three 6.66; the
+    # stored kernel's cooperative launches do not interleave (4.82 vs 5.19), so it runs one at a time
+    n_streams = max(1, args.streams) if args.streams else (2 if args.kernel != "stored" else 1)
+    tstreams = [torch.cuda.Stream() for _ in range(n_streams)]
+    pipe = Pipeline(local_rank, n_streams, make_stream=lambda k: tstreams[k].cuda_stream)
+    ctx = pipe.contexts[0]
     _lib._contexts[local_rank] = ctx
     online = args.kernel != "stored"
     prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_ONLINE if online else _lib.KERNEL_STORED,
@@ -328,48 +330,92 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- leg 1: inputs resident in HBM, CUDA events on the library's stream ---------------------
-    dp = DevicePair(ctx, torch, max_i, max_j, args.kernel)
-    for s in range(args.warmup):
-        dp.load(*coords[mine[s]])
-        dp.run(prm)
+    # ---- leg 1: inputs resident in HBM, CUDA events on the library's streams ---------------------
+    # Every step's coordinates are placed in HBM before the timed region.  Worker k (one library context and
+    # CUDA stream each) runs steps k, k + streams, ...; the timed region spans from the earliest start event
+    # to the latest end event over all streams.
+    dev = "cuda:%d" % local_rank
+    resident = {}
+    for p in set(mine):
+        x0, x1, g = coords[p]
+        resident[p] = (torch.from_numpy(x0.ravel()).to(dev), torch.from_numpy(x1.ravel()).to(dev),
+                       torch.from_numpy(g).to(dev))
+    dps = [DevicePair(pipe.contexts[k], torch, max_i, max_j, args.kernel) for k in range(n_streams)]
+
+    def worker_steps(k, first, last, timed):
+        """Steps first + k, first + k + streams, ... < last on context k.  Returns per-solve infos."""
+        dp, st = dps[k], tstreams[k]
+        out = []
+        with torch.cuda.stream(st):
+            if timed:
+                starts[k].record(st)
+            for s in range(first + k, last, n_streams):
+                dp.attach(mine[s], *resident[mine[s]])
+                out.append((mine[s], dp.run(prm)))
+            if timed:
+                ends[k].record(st)
+        return out
+
+    def run_block(first, last, timed):
+        threads, results = [], [None] * n_streams
+
+        def body(k):
+            results[k] = worker_steps(k, first, last, timed)
+        for k in range(n_streams):
+            t = threading.Thread(target=body, args=(k,))
+            t.start()
+            threads.append(t)
+        for t in threads:
+            t.join()
+        return [r for part in results for r in part]
+
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(n_streams)]
+    run_block(0, args.warmup, False)
+    big = max(set(mine), key=lambda p: p[0] * p[1])
+    for k in range(n_streams):                 # size every context's grow-only workspaces once, outside the timing
+        with torch.cuda.stream(tstreams[k]):
+            dps[k].attach(big, *resident[big])
+            dps[k].run(prm)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    gpu_ms = 0.0
+    done = run_block(args.warmup, total, True)
+    torch.cuda.synchronize()
+    gpu_ms = max(a.elapsed_time(b) for a in starts for b in ends)
+    barrier()
+    clocks = sampler.stop()
     iters = launches = 0
     mv_bytes = mv_launch = 0
     solve_ms = 0.0
     entry_iters = 0.0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for s in range(args.warmup, total):
-        dp.load(*coords[mine[s]])           # synthetic coordinates placed in HBM outside the timed region
-        ev0.record(stream)
-        infos = dp.run(prm)
-        ev1.record(stream)
-        ev1.synchronize()
-        gpu_ms += ev0.elapsed_time(ev1)
+    for (n0, n1, _), infos in done:
         for inf in infos:
             iters += inf["iters"]
             launches += inf["launches"]
             solve_ms += inf["gpu_ms"]
-            entry_iters += float(inf["iters"]) * dp.I * dp.J
-            b, n = matvec_bytes(inf, dp.I, dp.J, dp.J <= 23040)
-            mv_bytes += b
-            mv_launch += n
+            entry_iters += float(inf["iters"]) * n0 * n1
+            b_, n_ = matvec_bytes(inf, n0, n1, n1 <= 23040)
+            mv_bytes += b_
+            mv_launch += n_
         launches += 6 * 2 + 1 + 2 + 1       # median passes, cost (+pad), coupling
-    barrier()
-    clocks = sampler.stop()
     t_dev = max_over_ranks(gpu_ms / 1e3)
     total_steps = args.steps * world
     value = total_steps / t_dev
     iters_all = sum_over_ranks(iters)
 
     # ---- leg 2: end to end through the host-buffer C ABI ---------------------------------------
-    del dp
+    del dps, resident
+    for c in pipe.contexts:
+        c.lib.wotb_release_workspace(c.handle)
     torch.cuda.empty_cache()
+    # n_streams solves on the SMs plus one more context whose coupling is crossing PCIe meanwhile
+    # (Pipeline compute_slots; a step is still one day-pair through the host-buffer call)
+    n_e2e = n_streams + 1 if n_streams > 1 else 1
+    pipe2 = Pipeline(local_rank, n_e2e, compute_slots=n_streams if n_e2e > n_streams else 0)
+    biggest = max(set(mine), key=lambda p: p[0] * p[1])
     pin_in = {}
-    for p in set(mine[args.warmup:] + mine[:1]):
+    for p in set(mine[args.warmup:] + [biggest]):
         x0, x1, g = coords[p]
         bufs = []
         for arr in (x0, x1, g):
@@ -377,26 +423,50 @@ def run_ours(args, rank, world, local_rank):
             pa[...] = arr
             bufs.append(pa)
         pin_in[p] = bufs
-    out = _pinned.empty((max_i * max_j,), np.float64)
+    outs = [_pinned.empty((max_i * max_j,), np.float64) for _ in range(n_e2e)]
 
-    def e2e_step(p):
+    def e2e_step(k, p, growth_iters=GROWTH_ITERS):
         x0, x1, g = pin_in[p]
-        view = out[: p[0] * p[1]].reshape(p[0], p[1])
-        wot_ot.solve_coords(x0, x1, g, _lib.SOLVER_DUALITY_GAP, growth_iters=GROWTH_ITERS, kernel=args.kernel,
-                            out=view, device=local_rank, **DEFAULTS)
+        view = outs[k][: p[0] * p[1]].reshape(p[0], p[1])
+        wot_ot.solve_coords(x0, x1, g, _lib.SOLVER_DUALITY_GAP, growth_iters=growth_iters, kernel=args.kernel,
+                            out=view, ctx=pipe2.contexts[k], **DEFAULTS)
 
-    e2e_step(mine[0])                        # warm the pinned bounce paths and workspaces
+    def e2e_block(steps_of):
+        # worker k owns context k and output buffer k; it takes the next step from a shared counter
+        threads = []
+        for k in range(n_e2e):
+            t = threading.Thread(target=steps_of, args=(k,))
+            t.start()
+            threads.append(t)
+        for t in threads:
+            t.join()
+
+    e2e_block(lambda k: e2e_step(k, biggest, 1))     # warm every context's workspaces on the largest pair
     barrier()
+    next_step = [args.warmup]
+    lock = threading.Lock()
+
+    def timed_steps(k):
+        while True:
+            with lock:
+                s = next_step[0]
+                next_step[0] += 1
+            if s >= total:
+                return
+            e2e_step(k, mine[s])
+
     t0 = time.perf_counter()
+    e2e_block(timed_steps)
     h2d = d2h = 0
     for s in range(args.warmup, total):
         p = mine[s]
-        e2e_step(p)
         h2d += (p[0] + p[1]) * D * 8 + p[0] * 8
         d2h += p[0] * p[1] * 8 + (GROWTH_ITERS + 1) * p[0] * 8 + (p[0] + p[1]) * 8
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_steps / t_e2e
+    pipe2.close()
+    del outs
 
     if rank != 0:
         if dist is not None:
@@ -434,14 +504,15 @@ def run_ours(args, rank, world, local_rank):
     roofline_online = online_pass_roofline(ctx, torch, ri, rj)
     if online:
         roofline = roofline_online
-        # all-in: every Sinkhorn iteration evaluates 2*I*J exponentials; solver device time includes operand
-        # packing, the convergence checks and the final row sums
-        roofline["in_solve_frac"] = 2.0 * entry_iters / (solve_ms * 1e-3) / roofline["peak"] / 1e12
+        # all-in: every Sinkhorn iteration evaluates 2*I*J exponentials; the denominator is the whole timed region
+        # (median, operand packing, convergence checks, final row sums and coupling included)
+        roofline["in_step_frac"] = 2.0 * entry_iters / (gpu_ms * 1e-3) / roofline["peak"] / 1e12
         other = ("roofline_stored", roofline_stored)
     else:
         roofline = roofline_stored
-        roofline["in_solve_gbs"] = mv_bytes / (solve_ms * 1e-3) / 1e9
-        roofline["in_solve_note"] = "bytes of K streamed by the timed steps / total solver device time incl. K builds and checks"
+        roofline["in_step_gbs"] = mv_bytes / (gpu_ms * 1e-3) / 1e9
+        roofline["in_step_note"] = ("bytes of K streamed by the Sinkhorn iterations of the timed steps / the whole timed "
+                                    "region (cost, median, K builds, checks and coupling included)")
         other = ("roofline_online", roofline_online)
 
     cpu = None
@@ -465,18 +536,24 @@ def run_ours(args, rank, world, local_rank):
                    "lambda2": 50, "l2": ("every pass recomputes I*J = 25M-400M entries from L2-resident operands; nothing is cached "
                           "between steps (each step is a different day-pair)" if online else
                           "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)"),
-                   "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale},
+                   "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale,
+                   "streams": n_streams,
+                   "streams_note": "day-pairs are independent: each GPU keeps `streams` of them in flight on separate "
+                                   "CUDA streams (wot_b200.pipeline) so one fills the other's kernel tails, checks "
+                                   "and copies; a step is still one day-pair"},
         "sinkhorn_iters_per_s": iters_all / t_dev,
         "sinkhorn_iters": int(iters_all),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "tmaps/s", "h2d_bytes_per_step": h2d // args.steps,
-                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps},
+                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "contexts": n_e2e, "compute_slots": n_streams if n_e2e > n_streams else 0},
         "gpu_launches": int(launches),
         "roofline": roofline,
         other[0]: other[1],
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    pipe.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -104,6 +104,12 @@ int wotb_sync(wotb_ctx *ctx);
 /* Bytes of device memory currently held by the context's workspaces. */
 size_t wotb_workspace_bytes(const wotb_ctx *ctx);
 void wotb_release_workspace(wotb_ctx *ctx);
+/* Process-wide: at most n host-buffer calls (wotb_transport_map_from_*_host) are in their solve phase at a
+ * time; a call gives its slot back before its coupling is copied to the host.  Used when several contexts
+ * are driven from several threads (wot_b200/pipeline.py): n + 1 contexts with n slots keep n solves on the
+ * SMs while one coupling crosses PCIe.  n <= 0 (default): no limit.  Not in the reference (its loop over
+ * day-pairs, ot_model.py:182-199, is serial); the day-pairs are independent. */
+void wotb_set_compute_slots(int32_t n);
 
 /* ---- cost: replaces OTModel.compute_default_cost_matrix, ot_model.py:242-253 ------------------
  * x0 [I,d], x1 [J,d] float64 row-major; scale [d] = singular values (the diagonal of `eigenvals`,

@@ -2,6 +2,9 @@
 // points that bracket the device path with the copies a reference-side caller needs.
 #include <stdarg.h>
 
+#include <condition_variable>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace wotb {
@@ -87,6 +90,41 @@ int online_rowsums(wotb_ctx *, const double *, int64_t, const double *, int64_t,
 int bench_mufu(wotb_ctx *, double *);
 int coupling_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const double *, double, double, void *, int64_t, int, double *, cudaStream_t);
+
+// Compute slots: with several contexts in flight (wot_b200.pipeline), at most `limit` host-buffer calls are in
+// their solve phase at a time; a call gives its slot back before the coupling travels to the host, so a third
+// context can push its coupling over PCIe while two others keep the SMs busy.  limit 0 = no limit.
+struct ComputeSlots {
+    std::mutex m;
+    std::condition_variable cv;
+    int limit = 0, used = 0;
+    void acquire() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return limit <= 0 || used < limit; });
+        ++used;
+    }
+    void release() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            --used;
+        }
+        cv.notify_one();
+    }
+};
+static ComputeSlots g_slots;
+
+struct SlotGuard {
+    bool held = false;
+    SlotGuard() {
+        g_slots.acquire();
+        held = true;
+    }
+    void release() {
+        if (held) g_slots.release();
+        held = false;
+    }
+    ~SlotGuard() { release(); }
+};
 
 static bool is_pinned(const void *p) {
     cudaPointerAttributes at;
@@ -236,6 +274,14 @@ int wotb_create(int device, void *cuda_stream, wotb_ctx **out) {
     return WOTB_OK;
 }
 
+void wotb_set_compute_slots(int32_t n) {
+    {
+        std::lock_guard<std::mutex> lk(g_slots.m);
+        g_slots.limit = n > 0 ? n : 0;
+    }
+    g_slots.cv.notify_all();
+}
+
 void wotb_release_workspace(wotb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -327,6 +373,7 @@ int wotb_transport_map_from_cost_host(wotb_ctx *ctx, const double *C_host, int64
     WOTB_REQUIRE(I >= 1 && J >= 1, "empty cost matrix");
     WOTB_REQUIRE(params->kernel == WOTB_KERNEL_STORED, "a caller-supplied cost matrix needs the stored kernel");
     WOTB_CUDA(cudaSetDevice(ctx->device));
+    SlotGuard slot;
     const int64_t ld = round_up(J, 32);
     WOTB_TRY(ctx->hC.reserve((size_t)I * ld * 4));
     float *C = ctx->hC.as<float>();
@@ -348,6 +395,8 @@ int wotb_transport_map_from_cost_host(wotb_ctx *ctx, const double *C_host, int64
                              return sinkhorn_stored(ctx, C, ld, I, J, G, params, f, g, rs, info);
                          }));
     const wotb_info &last = infos[growth_iters - 1];
+    WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    slot.release();
     if (tmap_host) {
         WOTB_TRY(stream_coupling_to_host(ctx, I, J, tmap_host, out_dtype, nullptr,
                                          [&](int64_t r0, int64_t nr, void *dev, double *rs) {
@@ -367,6 +416,7 @@ int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, in
     WOTB_REQUIRE(ctx && x0_host && x1_host && G_host && params && infos, "NULL argument");
     WOTB_REQUIRE(I >= 1 && J >= 1 && d >= 1, "empty input");
     WOTB_CUDA(cudaSetDevice(ctx->device));
+    SlotGuard slot;
     HostVecs hv;
     char *extra = nullptr;
     const size_t nx0 = (size_t)round_up(I * d, 32) * 8, nx1 = (size_t)round_up(J * d, 32) * 8;
@@ -390,6 +440,8 @@ int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, in
                                  return sinkhorn_stored(ctx, C, ld, I, J, G, params, f, g, rs, info);
                              }));
         const wotb_info &last = infos[growth_iters - 1];
+        WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        slot.release();
         if (tmap_host) {
             WOTB_TRY(stream_coupling_to_host(ctx, I, J, tmap_host, out_dtype, nullptr,
                                              [&](int64_t r0, int64_t nr, void *dev, double *rs) {
@@ -408,6 +460,8 @@ int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, in
                                  return sinkhorn_online(ctx, xs0, I, xs1, J, d, median, G, params, f, g, rs, info);
                              }));
         const wotb_info &last = infos[growth_iters - 1];
+        WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        slot.release();
         if (tmap_host) {
             WOTB_TRY(stream_coupling_to_host(ctx, I, J, tmap_host, out_dtype, nullptr,
                                              [&](int64_t r0, int64_t nr, void *dev, double *rs) {

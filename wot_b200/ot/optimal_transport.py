@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import threading
 
 import numpy as np
 
@@ -19,12 +20,27 @@ from .. import _lib, _pinned
 
 logger = logging.getLogger("wot")
 
-_last = {}
+_tls = threading.local()
 
 
 def last_solve_info():
-    """dict(infos=[per growth iteration], f, g, learned_growth, median) of the most recent solve."""
-    return _last
+    """dict(infos=[per growth iteration], f, g, learned_growth, median) of the most recent solve made by the
+    calling thread (the workers of wot_b200.pipeline each see their own)."""
+    if not hasattr(_tls, "last"):
+        _tls.last = {}
+    return _tls.last
+
+
+def resolve_kernel(kernel, n_i, n_j, d, epsilon=0.05):
+    """'auto' -> 'online' or 'stored'.  The online kernel (K recomputed tile by tile on tcgen05 + MUFU, nothing of
+    size I x J in memory) is the faster one on B200.  Its exponent is accumulated in fp32 (TMEM), so its error
+    grows like 1/epsilon: ~1e-5 at the default 0.05, ~5e-5 at 0.01, where couplings still hold 1e-4 but slowly
+    converging settings (large lambdas) end a few batches away from the reference
+    (tests/test_gpu_parity.py::test_sweep_settings_vs_oracle).  The stored kernel (fp32 K built from a float64
+    exponent, error ~1e-6 whatever epsilon) is therefore kept for final epsilon < 0.02 and for d > 46."""
+    if kernel != "auto":
+        return kernel
+    return "online" if d <= 46 and float(epsilon) >= 0.02 else "stored"
 
 
 def _kernel_id(kernel):
@@ -51,15 +67,16 @@ def _out_array(shape, out, out_dtype, pinned):
 
 
 def _record(infos, f, g, learned, median=None):
-    _last.clear()
-    _last.update(infos=[i.as_dict() for i in infos], f=f, g=g, learned_growth=learned, median=median)
+    last = last_solve_info()
+    last.clear()
+    last.update(infos=[i.as_dict() for i in infos], f=f, g=g, learned_growth=learned, median=median)
     for i in infos:
         if i.status == _lib.STATUS_MAX_ITER:
             logger.warning("Reached max_iter with duality gap still above threshold. Returning")
 
 
 def solve_cost(C_mat, G, solver_id, growth_iters=1, out=None, out_dtype=np.float64, want_tmap=True, pinned=True,
-               device=None, **params):
+               device=None, ctx=None, **params):
     """Growth loop on a caller-supplied cost matrix.  Returns (tmap or None, learned_growth [g+1, I])."""
     C_mat = np.ascontiguousarray(C_mat, dtype=np.float64)
     if C_mat.ndim != 2:
@@ -70,7 +87,7 @@ def solve_cost(C_mat, G, solver_id, growth_iters=1, out=None, out_dtype=np.float
         raise ValueError("G must have one entry per row of C")
     growth_iters = int(growth_iters)
     prm = _lib.make_params(solver=solver_id, **params)
-    ctx = _lib.context(device)
+    ctx = ctx or _lib.context(device)
     tmap = _out_array((n_i, n_j), out, out_dtype, pinned) if want_tmap else None
     learned = np.empty((growth_iters + 1, n_i))
     f, g = np.empty(n_i), np.empty(n_j)
@@ -84,8 +101,8 @@ def solve_cost(C_mat, G, solver_id, growth_iters=1, out=None, out_dtype=np.float
     return tmap, learned
 
 
-def solve_coords(x0, x1, G, solver_id, scale=None, growth_iters=1, kernel="stored", out=None, out_dtype=np.float64,
-                 want_tmap=True, pinned=True, device=None, **params):
+def solve_coords(x0, x1, G, solver_id, scale=None, growth_iters=1, kernel="auto", out=None, out_dtype=np.float64,
+                 want_tmap=True, pinned=True, device=None, ctx=None, **params):
     """Default cost (ot_model.py:242-253) + growth loop from local-PCA coordinates, all on the GPU."""
     x0 = np.ascontiguousarray(x0, dtype=np.float64)
     x1 = np.ascontiguousarray(x1, dtype=np.float64)
@@ -100,9 +117,14 @@ def solve_coords(x0, x1, G, solver_id, scale=None, growth_iters=1, kernel="store
         if scale.shape != (d,):
             raise ValueError("scale must have one entry per coordinate")
     growth_iters = int(growth_iters)
+    # final epsilon: epsilon0 * epsilon for the duality-gap schedule (:102-120), epsilon for fixed_iters (:184-185)
+    eps_final = float(params.get("epsilon", 0.05))
+    if solver_id == _lib.SOLVER_DUALITY_GAP:
+        eps_final *= float(params.get("epsilon0", 1.0))
+    kernel = resolve_kernel(kernel, n_i, n_j, d, eps_final)
     kernel_id, simt = _kernel_id(kernel)
     prm = _lib.make_params(solver=solver_id, kernel=kernel_id, online_simt=simt, **params)
-    ctx = _lib.context(device)
+    ctx = ctx or _lib.context(device)
     tmap = _out_array((n_i, n_j), out, out_dtype, pinned) if want_tmap else None
     learned = np.empty((growth_iters + 1, n_i))
     f, g = np.empty(n_i), np.empty(n_j)
@@ -156,7 +178,7 @@ def transport_stablev2(C, lambda1, lambda2, epsilon, scaling_iter, G, tau, epsil
 
 
 _SOLVER_IDS = {optimal_transport_duality_gap: _lib.SOLVER_DUALITY_GAP, transport_stablev2: _lib.SOLVER_FIXED_ITERS}
-_EXTRA_KEYS = ("out", "out_dtype", "pinned", "device", "use_graph", "fuse")
+_EXTRA_KEYS = ("out", "out_dtype", "pinned", "device", "ctx", "use_graph", "fuse")
 
 
 def _extras(ignored):
@@ -188,7 +210,7 @@ def compute_transport_matrix(solver, **params):
     if coords is not None and params.get("C") is None:
         x0, x1, scale = coords
         tmap, learned = solve_coords(x0, x1, params["G"], solver_id, scale=scale, growth_iters=growth_iters,
-                                     kernel=params.get("kernel", "stored"), **kw)
+                                     kernel=params.get("kernel", "auto"), **kw)
     else:
         tmap, learned = solve_cost(params["C"], params["G"], solver_id, growth_iters=growth_iters, **kw)
     params["G"] = learned[growth_iters - 1]

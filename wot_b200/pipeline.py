@@ -1,0 +1,82 @@
+"""Several transport maps in flight on one GPU.
+
+Day-pairs (ot_model.py:182-199) and sweep settings are independent, and one solve leaves the GPU idle in
+places: the tail and launch gap of every pass kernel (each is a one-wave grid that must drain before the next
+half-iteration can start), the convergence checks, the median selection, the copy of the coupling to the host.
+A second solve on its own CUDA stream fills those holes: both kernels are one CTA per SM, so the hardware hands
+every SM that a draining kernel frees to the other stream's kernel.  Measured on B200 (atlas-shaped config):
+see DESIGN.md section 7.
+
+`Pipeline(device, streams)` owns `streams` library contexts (one CUDA stream and workspace set each) and one
+worker thread per context; ctypes releases the GIL inside the library, so the workers really overlap.
+Results come back in submission order.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+from concurrent.futures import Future
+
+from . import _lib
+
+
+class Pipeline:
+    def __init__(self, device=None, streams=2, make_stream=None, compute_slots=0):
+        """`make_stream(k)` may return a raw cudaStream_t handle for context k (e.g. a torch stream's
+        .cuda_stream, kept alive by the caller); by default every context creates its own stream.
+        `compute_slots` n > 0: at most n host-buffer solves are in their solve phase at once (process-wide,
+        wotb_set_compute_slots); with streams = n + 1 the extra context overlaps its coupling's trip over PCIe
+        with the other contexts' solves."""
+        if streams < 1:
+            raise ValueError("streams must be >= 1")
+        _lib.load().wotb_set_compute_slots(int(compute_slots))
+        self._slots = int(compute_slots)
+        if device is None:
+            device = _lib.context().device
+        self.device = int(device)
+        self.contexts = [_lib.Context(self.device, make_stream(k) if make_stream else None) for k in range(streams)]
+        self._jobs = queue.Queue()
+        self._threads = [threading.Thread(target=self._work, args=(ctx,), daemon=True) for ctx in self.contexts]
+        for t in self._threads:
+            t.start()
+
+    def _work(self, ctx):
+        while True:
+            job = self._jobs.get()
+            if job is None:
+                return
+            fut, fn, args, kwargs = job
+            if not fut.set_running_or_notify_cancel():
+                continue
+            try:
+                fut.set_result(fn(ctx, *args, **kwargs))
+            except BaseException as exc:  # noqa: BLE001 - handed to the caller through the future
+                fut.set_exception(exc)
+
+    def submit(self, fn, *args, **kwargs):
+        """Run fn(ctx, *args, **kwargs) on the next free context; returns a concurrent.futures.Future."""
+        fut = Future()
+        self._jobs.put((fut, fn, args, kwargs))
+        return fut
+
+    def map(self, fn, items):
+        """fn(ctx, item) for every item, at most `streams` at a time; results in the order of `items`."""
+        futs = [self.submit(fn, item) for item in items]
+        return [f.result() for f in futs]
+
+    def close(self):
+        for _ in self._threads:
+            self._jobs.put(None)
+        for t in self._threads:
+            t.join()
+        for ctx in self.contexts:
+            ctx.close()
+        self.contexts = []
+        if self._slots:
+            _lib.load().wotb_set_compute_slots(0)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
