@@ -447,3 +447,30 @@ def test_pipeline_streams_match_serial(ot):
             np.testing.assert_array_equal(a[1], b[1])
             np.testing.assert_array_equal(a[2], b[2])
             assert a[3] == b[3]
+
+
+def test_compute_all_transport_maps_pipelined_equals_serial(ot, tmp_path):
+    """OTModel.compute_all_transport_maps (ot_model.py:124-201) with day-pairs in flight on several streams writes
+    the same files, bit for bit, as the serial loop (streams=1), including the row order of '{prefix}_g.txt'."""
+    import os
+    from wot_b200 import synthetic
+    from wot_b200._anndata import AnnData
+    X, day, growth = synthetic.expression_matrix([310, 280, 350, 300, 330], n_genes=80, seed=21)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    var = pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])])
+    outs = {}
+    for streams in (1, 2):
+        model = ot.OTModel(AnnData(X.copy(), obs.copy(), var.copy()), growth_iters=2, local_pca=10, streams=streams)
+        d = tmp_path / ("s%d" % streams)
+        d.mkdir()
+        model.compute_all_transport_maps(tmap_out=str(d / "tm"), output_file_format="npz")
+        outs[streams] = d
+    names = sorted(os.listdir(outs[1]))
+    assert names == sorted(os.listdir(outs[2])) and len(names) == 5 and "tm_g.txt" in names
+    for n in names:
+        if n.endswith(".npz"):
+            a, b = np.load(outs[1] / n, allow_pickle=True), np.load(outs[2] / n, allow_pickle=True)
+            np.testing.assert_array_equal(a["X"], b["X"])
+            np.testing.assert_array_equal(a["obs_values"], b["obs_values"])
+        else:
+            assert (outs[1] / n).read_text() == (outs[2] / n).read_text()

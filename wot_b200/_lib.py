@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import threading
 
 import numpy as np
 
@@ -160,10 +161,15 @@ class Context:
 
 
 _contexts = {}
+_thread = threading.local()      # .ctx: the context a pipeline worker thread is bound to
 
 
 def context(device=None):
-    """The process-wide context of `device` (default: LOCAL_RANK, else 0)."""
+    """The context library calls of this thread use: the one a wot_b200.pipeline worker is bound to, else the
+    process-wide context of `device` (default: LOCAL_RANK, else 0)."""
+    bound = getattr(_thread, "ctx", None)
+    if bound is not None and bound.handle and (device is None or int(device) == bound.device):
+        return bound
     if device is None:
         device = int(os.environ.get("WOT_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
     ctx = _contexts.get(device)

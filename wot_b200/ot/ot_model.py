@@ -45,6 +45,9 @@ class OTModel:
     **kwargs
         config, cell_filter, gene_filter, cell_day_filter, ncounts, ncells, solver, parameters, and any
         OT parameter (epsilon, lambda1, lambda2, growth_iters, local_pca, ...).
+        Additive (not in the reference): `streams` (default 2) = day-pairs compute_all_transport_maps keeps in
+        flight on the GPU (wot_b200.pipeline; 1 = the reference's serial loop), `kernel` = 'auto' | 'stored' |
+        'online'.
     """
 
     def __init__(self, matrix, day_field="day", covariate_field="covariate", growth_rate_field="cell_growth_rate",
@@ -59,6 +62,7 @@ class OTModel:
         day_filter = kwargs.pop("cell_day_filter", None)
         ncounts = kwargs.pop("ncounts", None)
         ncells = kwargs.pop("ncells", None)
+        self.streams = int(kwargs.pop("streams", 2))
         self.matrix = _io.filter_adata(self.matrix, obs_filter=cell_filter, var_filter=gene_filter)
         if day_filter is not None:
             keep_days = [float(t) for t in day_filter.split(",")] if isinstance(day_filter, str) else day_filter
@@ -151,6 +155,7 @@ class OTModel:
             cost_matrices = [None] * len(day_pairs)
         growth_frames = []
         keep_growth = self.ot_config.get("growth_iters", 1) > 1
+        todo = []
         for day_pair, cost_matrix in zip(day_pairs, cost_matrices):
             if not with_covariates:
                 name = tmap_prefix + "_{}_{}".format(*day_pair)
@@ -160,10 +165,28 @@ class OTModel:
             if os.path.exists(output_file) and not overwrite:
                 logger.info("Found existing tmap at " + output_file + ". ")
                 continue
+            todo.append((day_pair, cost_matrix, output_file))
+
+        def one(day_pair, cost_matrix, output_file):
             tmap = self.compute_transport_map(*day_pair, cost_matrix=cost_matrix)
+            if tmap is None:
+                return None
             _io.write_dataset(tmap, output_file, output_format=output_file_format)
-            if keep_growth:
-                growth_frames.append(tmap.obs)
+            return tmap.obs if keep_growth else None
+
+        ours = self.solver in (_ot.optimal_transport_duality_gap, _ot.transport_stablev2)
+        if ours and self.streams > 1 and len(todo) > 1:
+            # the day-pairs are independent (the reference loops over them serially, :182-199): keep `streams`
+            # solves on the SMs and one more context whose coupling is travelling to the host; local PCA of the
+            # next pairs runs on the host meanwhile.  Files and the row order of '{prefix}_g.txt' are those of
+            # the serial loop.
+            from ..pipeline import Pipeline
+            with Pipeline(streams=self.streams + 1, compute_slots=self.streams) as pipe:
+                futures = [pipe.submit(lambda ctx, job=job: one(*job)) for job in todo]
+                frames = [f.result() for f in futures]
+        else:
+            frames = [one(*job) for job in todo]
+        growth_frames = [f for f in frames if f is not None]
         if growth_frames:
             pd.concat(growth_frames).to_csv(os.path.join(tmap_dir, tmap_prefix + "_g.txt"), sep="\t",
                                             index_label="id")

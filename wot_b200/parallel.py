@@ -78,13 +78,26 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
     mine = [todo[q] for q in shard_units(costs, world)[rank]]
     keep_growth = model.ot_config.get("growth_iters", 1) > 1
     frames = {}
-    for k in mine:
+
+    def one(k):
         tmap = model.compute_transport_map(*day_pairs[k], cost_matrix=cost_matrices[k])
         if tmap is None:
-            continue
+            return None
         _io.write_dataset(tmap, files[k], output_format=output_file_format)
-        if keep_growth:
-            frames[k] = tmap.obs
+        return tmap.obs if keep_growth else None
+
+    from .ot import optimal_transport as _ot
+    streams = int(getattr(model, "streams", 1))
+    if model.solver in (_ot.optimal_transport_duality_gap, _ot.transport_stablev2) and streams > 1 and len(mine) > 1:
+        # this rank's pairs, `streams` solves in flight on its GPU plus one coupling on its way to the host
+        from .pipeline import Pipeline
+        with Pipeline(device=int(os.environ.get("LOCAL_RANK", "0")), streams=streams + 1, compute_slots=streams) as pipe:
+            got = pipe.map(lambda ctx, k: one(k), mine)
+    else:
+        got = [one(k) for k in mine]
+    for k, obs in zip(mine, got):
+        if obs is not None:
+            frames[k] = obs
     if keep_growth:
         gathered = [frames]
         if world > 1:

@@ -41,6 +41,7 @@ class Pipeline:
             t.start()
 
     def _work(self, ctx):
+        _lib._thread.ctx = ctx       # library calls made on this thread without an explicit ctx use this context
         while True:
             job = self._jobs.get()
             if job is None:
