@@ -153,6 +153,9 @@ class WorkQueue:
         return self.order[k]
 
 
+_sweep_calls = 0
+
+
 def expected_sweep_cost(setting):
     """Relative cost guess used only to order the queue: iteration counts grow roughly like
     (lambda1 + lambda2) / epsilon at fixed shape (70 .. >30k iterations)."""
@@ -173,6 +176,9 @@ def parameter_sweep(x0, x1, G, settings, solve=None, group=None, store=None, que
         solve = _sweep_solve_gpu
     order = sorted(range(len(settings)), key=lambda k: (-expected_sweep_cost(settings[k]), k))
     mine = {}
+    global _sweep_calls
+    _sweep_calls += 1                  # every rank makes the same sequence of calls: a fresh counter per sweep
+    queue_key = "%s/%d" % (queue_key, _sweep_calls)
     if world > 1:
         import torch.distributed as dist
         dist.barrier(group=group)      # start drawing together
