@@ -111,6 +111,21 @@ void wotb_release_workspace(wotb_ctx *ctx);
  * day-pairs, ot_model.py:182-199, is serial); the day-pairs are independent. */
 void wotb_set_compute_slots(int32_t n);
 
+/* ---- local PCA: replaces compute_pca, wot/ot/util.py:240-255 -------------------
+ * m1 [n1, genes], m2 [n2, genes] float64 row-major (the two days' expression rows, util.py:241-244).
+ * Computes what sklearn.decomposition.PCA(k, random_state=58951).fit(x.T) computes with its randomized
+ * solver (the one svd_solver='auto' picks when max(shape) > 500 and k < 0.8 min(shape)): x = vstack - gene
+ * means (:245-246), per-cell centring, randomized range finder with `size` = k + n_oversamples (10) columns
+ * and n_iter power iterations (7 if k < 0.1 min(shape) else 4), small SVD.  q0 [min(genes, n1+n2) rows... see
+ * below, size] is the Gaussian test matrix numpy.random.RandomState(58951).normal(size=(short side, size))
+ * made by the caller so that the result equals scikit-learn's up to sign and roundoff; "short side" is genes
+ * when genes < n1 + n2, else n1 + n2.  Outputs: comp [n1 + n2, k] = pca.components_.T (util.py:250),
+ * singular_values [k] (ot_model.py:301), gene_means [genes] (util.py:245; may be NULL), gpu_ms (may be NULL).
+ * Everything is float64 and reduced in a fixed order (deterministic). */
+int wotb_pca_host(wotb_ctx *ctx, const double *m1_host, int64_t n1, const double *m2_host, int64_t n2, int64_t genes,
+                  int32_t k, const double *q0_host, int32_t size, int32_t n_iter, double *comp_host,
+                  double *singular_values_host, double *gene_means_host, double *gpu_ms);
+
 /* ---- cost: replaces OTModel.compute_default_cost_matrix, ot_model.py:242-253 ------------------
  * x0 [I,d], x1 [J,d] float64 row-major; scale [d] = singular values (the diagonal of `eigenvals`,
  * ot_model.py:301) or NULL.  Distances are sum_k (x0_ik s_k - x1_jk s_k)^2 in float64 with the

@@ -474,3 +474,26 @@ def test_compute_all_transport_maps_pipelined_equals_serial(ot, tmp_path):
             np.testing.assert_array_equal(a["obs_values"], b["obs_values"])
         else:
             assert (outs[1] / n).read_text() == (outs[2] / n).read_text()
+
+
+@pytest.mark.parametrize("cells,genes,k", [([600, 700], 300, 30), ([900, 800], 1479, 30), ([300, 280], 700, 10),
+                                           ([3000, 3200], 1000, 30), ([5000, 7000], 1479, 30)])
+def test_gpu_pca_vs_sklearn(cells, genes, k):
+    """local PCA on the GPU (csrc/pca.cu) against the reference's own call on scikit-learn
+    (wot/ot/util.py:240-255): same signs, components and singular values to roundoff, the default cost built from
+    them (ot_model.py:242-253) to 1e-9."""
+    from oracle import wot_oracle
+    from wot_b200 import synthetic
+    from wot_b200.ot import util
+    X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=3)
+    m1, m2 = X[day == 0], X[day == 1]
+    p1, p2, pca, mu = util.compute_pca_sklearn(m1, m2, k)
+    q1, q2, gpca, mu2 = util.compute_pca(m1, m2, k)
+    assert isinstance(gpca, util.LocalPCA)            # 'auto' took the GPU path
+    np.testing.assert_allclose(mu2, mu, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(gpca.singular_values_, pca.singular_values_, rtol=1e-10)
+    np.testing.assert_allclose(np.vstack([q1, q2]), np.vstack([p1, p2]), rtol=0, atol=1e-8)
+    if sum(cells) <= 7000:
+        want = wot_oracle.compute_default_cost_matrix(p1, p2, np.diag(pca.singular_values_))
+        got = wot_oracle.compute_default_cost_matrix(q1, q2, np.diag(gpca.singular_values_))
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11)

@@ -107,3 +107,24 @@ def test_marginal_gap_identity():
     pri2, dua2 = orc.gap_from_marginals(R.sum(1), R.sum(0), u + eps * np.log(a), v + eps * np.log(b),
                                         K0.sum(), G, q, eps, l1, l2)
     assert abs(pri - pri2) < 1e-13 * abs(pri) and abs(dua - dua2) < 1e-13 * abs(dua)
+
+
+@pytest.mark.parametrize("cells,genes,k", [([600, 700], 300, 30), ([450, 420], 1479, 30), ([300, 280], 700, 10)])
+def test_pca_restatement_matches_sklearn(cells, genes, k):
+    """oracle/pca_oracle.py (randomized range finder with Cholesky-QR normalisation, the form the CUDA path runs)
+    against the reference's own call, sklearn PCA(k, random_state=58951).fit(x.T) (wot/ot/util.py:240-255), on the
+    installed scikit-learn: singular values and the default cost matrix built from the coordinates
+    (ot_model.py:242-253; sign-invariant) agree to roundoff.  Covers both orientations of transpose='auto'."""
+    from oracle import pca_oracle, wot_oracle
+    from wot_b200 import synthetic
+    from wot_b200.ot import util
+    X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=3)
+    m1, m2 = X[day == 0], X[day == 1]
+    assert pca_oracle.solver_choice(genes, sum(cells), k) == util.sklearn_solver_choice(genes, sum(cells), k) == "randomized"
+    p1, p2, pca, mu = util.compute_pca_sklearn(m1, m2, k)
+    q1, q2, sv, mu2 = pca_oracle.compute_pca(m1, m2, k)
+    np.testing.assert_allclose(mu2, mu, rtol=0, atol=1e-14)
+    np.testing.assert_allclose(sv, pca.singular_values_, rtol=1e-12)
+    want = wot_oracle.compute_default_cost_matrix(p1, p2, np.diag(pca.singular_values_))
+    got = wot_oracle.compute_default_cost_matrix(q1, q2, np.diag(sv))
+    np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)

@@ -1,24 +1,108 @@
-"""Local PCA, the producer of the hot path's inputs (reference: wot/ot/util.py:240-255).  Kept on the
-CPU / scikit-learn so the GPU path and the reference see identical coordinates."""
+"""Local PCA, the producer of the hot path's inputs (reference: wot/ot/util.py:240-255).
+
+`compute_pca` keeps the reference's signature and return tuple.  Where scikit-learn's PCA(svd_solver='auto') would
+run its randomized solver (always at atlas shapes: max(shape) > 500 and k < 0.8 min(shape)) the same arithmetic
+runs on the GPU (csrc/pca.cu, float64): same centring, same Gaussian test matrix (numpy RandomState(58951)), same
+number of power iterations, same sign convention, so the components equal scikit-learn's to roundoff
+(tests: cost matrices agree to 1e-9).  Tiny problems, for which scikit-learn itself switches to an exact LAPACK
+solver, stay on scikit-learn.
+"""
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import scipy.sparse
-import sklearn.decomposition
+
+from .. import _lib
+
+RANDOM_STATE = 58951          # util.py:248
+N_OVERSAMPLES = 10            # sklearn PCA default
 
 
-def compute_pca(m1, m2, n_components):
-    """Joint PCA of two cell populations, fitted on the TRANSPOSED, gene-mean-centred matrix.
+class LocalPCA:
+    """The attributes of the fitted sklearn PCA that the transport-map path reads (ot_model.py:297-301)."""
 
-    Returns (pca_1 [I, n], pca_2 [J, n], fitted PCA, gene means), like util.py:240-255.
-    """
-    dense = [m.toarray() if scipy.sparse.isspmatrix(m) else np.asarray(m) for m in (m1, m2)]
+    def __init__(self, components, singular_values, n_samples, cell_means, gpu_ms):
+        self.components_ = components                  # [k, cells]
+        self.singular_values_ = singular_values        # [k]
+        self.n_components_ = self.n_components = components.shape[0]
+        self.explained_variance_ = singular_values ** 2 / (n_samples - 1)
+        self.mean_ = cell_means
+        self.gpu_ms = gpu_ms
+
+
+def sklearn_solver_choice(n_samples, n_features, k):
+    """Which solver sklearn 1.x PCA(svd_solver='auto').fit picks for an (n_samples, n_features) matrix
+    (sklearn/decomposition/_pca.py::_fit)."""
+    if n_features <= 1000 and n_samples >= 10 * n_features:
+        return "covariance_eigh"
+    if max(n_samples, n_features) <= 500:
+        return "full"
+    if 1 <= k < 0.8 * min(n_samples, n_features):
+        return "randomized"
+    return "full"
+
+
+def _dense(m):
+    return m.toarray() if scipy.sparse.isspmatrix(m) else np.asarray(m)
+
+
+def compute_pca_sklearn(m1, m2, n_components):
+    """The reference's own arithmetic (util.py:240-255) on scikit-learn."""
+    import sklearn.decomposition
+    dense = [_dense(m1), _dense(m2)]
     stacked = np.vstack(dense)
     gene_means = stacked.mean(axis=0)
     stacked = stacked - gene_means
     n_components = min(n_components, stacked.shape[0])  # cannot exceed the number of cells
-    pca = sklearn.decomposition.PCA(n_components=n_components, random_state=58951)
+    pca = sklearn.decomposition.PCA(n_components=n_components, random_state=RANDOM_STATE)
     pca.fit(stacked.T)
     loadings = pca.components_.T
     n1 = dense[0].shape[0]
     return loadings[:n1], loadings[n1:n1 + dense[1].shape[0]], pca, gene_means
+
+
+def compute_pca_gpu(m1, m2, n_components, ctx=None):
+    """Randomized-solver path of util.py:240-255 on the GPU (wotb_pca_host)."""
+    a = np.ascontiguousarray(_dense(m1), dtype=np.float64)
+    b = np.ascontiguousarray(_dense(m2), dtype=np.float64)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("m1 and m2 must be 2-D with the same number of genes")
+    n1, n2, genes = a.shape[0], b.shape[0], a.shape[1]
+    cells = n1 + n2
+    k = min(int(n_components), cells)
+    size = k + N_OVERSAMPLES
+    n_iter = 7 if k < 0.1 * min(genes, cells) else 4                   # randomized_svd(n_iter='auto')
+    short = genes if genes < cells else cells                          # transpose='auto'
+    q0 = np.random.RandomState(RANDOM_STATE).normal(size=(short, size))   # randomized_range_finder's test matrix
+    comp = np.empty((cells, k))
+    sv = np.empty(k)
+    gene_means = np.empty(genes)
+    ms = C.c_double()
+    ctx = ctx or _lib.context()
+    _lib.check(ctx.lib.wotb_pca_host(ctx.handle, _lib.ptr(a), n1, _lib.ptr(b), n2, genes, k, _lib.ptr(q0), size, n_iter,
+                                     _lib.ptr(comp), _lib.ptr(sv), _lib.ptr(gene_means), C.byref(ms)))
+    # svd_flip(u_based_decision=False): the largest-magnitude loading of every component is positive
+    top = np.argmax(np.abs(comp), axis=0)
+    comp *= np.sign(comp[top, np.arange(k)])
+    pca = LocalPCA(comp.T, sv, genes, None, ms.value)
+    return comp[:n1], comp[n1:], pca, gene_means
+
+
+def compute_pca(m1, m2, n_components, backend="auto"):
+    """Joint PCA of two cell populations, fitted on the TRANSPOSED, gene-mean-centred matrix.
+
+    Returns (pca_1 [I, n], pca_2 [J, n], fitted PCA, gene means), like util.py:240-255.
+    backend: 'auto' (GPU where scikit-learn would use its randomized solver), 'gpu', 'sklearn'."""
+    if backend not in ("auto", "gpu", "sklearn"):
+        raise ValueError("backend must be 'auto', 'gpu' or 'sklearn'")
+    n1, n2 = m1.shape[0], m2.shape[0]
+    genes = m1.shape[1]
+    k = min(int(n_components), n1 + n2)
+    if backend == "auto":
+        fits = k + N_OVERSAMPLES <= min(64, genes, n1 + n2)
+        backend = "gpu" if fits and sklearn_solver_choice(genes, n1 + n2, k) == "randomized" else "sklearn"
+    if backend == "sklearn":
+        return compute_pca_sklearn(m1, m2, n_components)
+    return compute_pca_gpu(m1, m2, n_components)
