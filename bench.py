@@ -501,7 +501,12 @@ def run_ours(args, rank, world, local_rank):
         "fused_iter_ms": ms_fused, "row_ms": ms_row, "col_ms": ms_col,
         "row_gbs": alg / (ms_row * 1e-3) / 1e9, "col_gbs": alg / (ms_col * 1e-3) / 1e9,
     }
-    roofline_online = online_pass_roofline(ctx, torch, ri, rj)
+    roofline_online = online_pass_roofline(ctx, torch, ri, rj)      # launch mode of the timed region
+    if n_streams > 1:
+        # one solve at a time launches the passes with programmatic dependent launch (the pipeline turns it off)
+        ctx.lib.wotb_set_pdl(1)
+        roofline_online["frac_single_stream_pdl"] = online_pass_roofline(ctx, torch, ri, rj)["frac"]
+        ctx.lib.wotb_set_pdl(0)
     if online:
         roofline = roofline_online
         # all-in: every Sinkhorn iteration evaluates 2*I*J exponentials; the denominator is the whole timed region

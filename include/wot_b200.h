@@ -110,6 +110,10 @@ void wotb_release_workspace(wotb_ctx *ctx);
  * SMs while one coupling crosses PCIe.  n <= 0 (default): no limit.  Not in the reference (its loop over
  * day-pairs, ot_model.py:182-199, is serial); the day-pairs are independent. */
 void wotb_set_compute_slots(int32_t n);
+/* Process-wide: launch the online pass kernels with programmatic dependent launch (default on: the next
+ * half-iteration's CTAs set themselves up while the current kernel drains; +3 % with one solve at a time).
+ * wot_b200/pipeline.py turns it off while several solves share the GPU (it costs 2 % there). */
+void wotb_set_pdl(int32_t on);
 
 /* ---- local PCA: replaces compute_pca, wot/ot/util.py:240-255 -------------------
  * m1 [n1, genes], m2 [n2, genes] float64 row-major (the two days' expression rows, util.py:241-244).

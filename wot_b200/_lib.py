@@ -56,6 +56,7 @@ SIGNATURES = {
     "wotb_workspace_bytes": (C.c_size_t, [_P]),
     "wotb_release_workspace": (None, [_P]),
     "wotb_set_compute_slots": (None, [C.c_int32]),
+    "wotb_set_pdl": (None, [C.c_int32]),
     "wotb_pca_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                 _P]),
     "wotb_cost_median_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, C.POINTER(_D)]),

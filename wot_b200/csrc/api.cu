@@ -282,6 +282,8 @@ void wotb_set_compute_slots(int32_t n) {
     g_slots.cv.notify_all();
 }
 
+void wotb_set_pdl(int32_t on) { wotb::set_pdl(on != 0); }
+
 void wotb_release_workspace(wotb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);

@@ -98,4 +98,5 @@ namespace wotb {
 int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64_t J, const double *G,
                     const wotb_params *prm, double *f, double *g, double *rowsum, wotb_info *info);
 int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, double *ms_col, double *ms_fused);
+void set_pdl(bool on);
 }  // namespace wotb

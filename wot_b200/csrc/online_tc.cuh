@@ -35,6 +35,7 @@
 #pragma once
 
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "online_pass.cuh"
 
@@ -339,15 +340,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 template <bool COLPASS, int KSEG, int EW>
 __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     k_online_tc(TcArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
-    if (mode == 0 || mode == 4) {
-        if (!iteration_active(ctrl)) return;
-    } else if (mode == 1) {
-        if (!gap_rows_wanted(ctrl)) return;
-    } else if (mode == 3) {
-        if (ctrl->done || !ctrl->need_build || ctrl->solver != WOTB_SOLVER_DUALITY_GAP ||
-            ctrl->stage != WOTB_N_STAGES - 1)
-            return;
-    }
     constexpr int RB = kTcRowBlocks, NT = kTcN;
     constexpr int kEpiThreads = RB * EW * 32;
     constexpr int NCH = 4 / (EW / 4);  // 32-column chunks per tile and warp
@@ -402,7 +394,23 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
-    if (wid == 0) {
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) touched only this CTA's own
+    // resources and may have run while the previous kernel in the stream was still draining; from here on the
+    // state written by that kernel (SolveCtrl, offsets in the operand slots, scalings) is read.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool active = true;
+    if (mode == 0 || mode == 4) {
+        active = iteration_active(ctrl);
+    } else if (mode == 1) {
+        active = gap_rows_wanted(ctrl);
+    } else if (mode == 3) {
+        active = !(ctrl->done || !ctrl->need_build || ctrl->solver != WOTB_SOLVER_DUALITY_GAP ||
+                   ctrl->stage != WOTB_N_STAGES - 1);
+    }
+
+    if (!active) {
+        // nothing to do (batch finished, solver done, ...): fall through to the TMEM release
+    } else if (wid == 0) {
         if (lane == 0) {
             // ===== TMA producer: per out-block segment the two A blocks, then the B ring =====
             const unsigned char *srcA = reinterpret_cast<const unsigned char *>(A.opA);
@@ -428,6 +436,9 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                 }
                 g += n_in_seg;
             }
+            // every operand of this CTA is on its way: the next kernel in the stream may be scheduled onto SMs as
+            // they free up (it waits at its own griddepcontrol.wait until this grid has completed)
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         }
     } else if (wid <= RB) {
         // ===== MMA issuers: warp 1 + rb feeds the accumulators of row block rb.  The whole warp runs the loop (uniform
@@ -684,13 +695,45 @@ inline int tc_configure(const TcPlan &plan) {
     return WOTB_OK;
 }
 
+// Programmatic dependent launch between consecutive passes (and whatever precedes them in the stream): the next
+// kernel's CTAs are scheduled as SMs free up and set themselves up while the current one drains.  Measured on B200
+// (profiles/r1m): one solve at a time 48.0 -> 45.6 us per 12.5k x 12.4k pass, 6.41 -> 6.62 tmaps/s; with two solves
+// in flight on separate streams it LOSES (7.31 -> 7.14): SMs freed by a draining kernel are better used by the
+// other stream's CTAs than by waiting ones, so wot_b200.pipeline turns it off (wotb_set_pdl).  WOTB_NO_PDL=1 in
+// the environment sets the initial state to off.
+inline int &tc_pdl_flag() {
+    static int use = -1;
+    return use;
+}
+inline bool tc_use_pdl() {
+    int &use = tc_pdl_flag();
+    if (use < 0) {
+        const char *e = getenv("WOTB_NO_PDL");
+        use = (e && e[0] == '1') ? 0 : 1;
+    }
+    return use == 1;
+}
+
+template <bool COLPASS, int K, int E>
+inline void tc_launch_one(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
+                          int mode, double *rowsum_out) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(128 + kTcRowBlocks * E * 32), cfg.dynamicSmemBytes = plan.smem, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr, cfg.numAttrs = tc_use_pdl() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_online_tc<COLPASS, K, E>, A, V, ctrl, mode, rowsum_out);
+}
+
 template <bool COLPASS>
 inline void tc_launch(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
                       int mode, double *rowsum_out) {
-#define WOTB_TC_CASE(K, E)                                                                                        \
-    if (plan.kseg == K && plan.ew == E) {                                                                         \
-        k_online_tc<COLPASS, K, E><<<grid, 128 + kTcRowBlocks * E * 32, plan.smem, st>>>(A, V, ctrl, mode, rowsum_out); \
-        return;                                                                                                   \
+#define WOTB_TC_CASE(K, E)                                                                   \
+    if (plan.kseg == K && plan.ew == E) {                                                    \
+        tc_launch_one<COLPASS, K, E>(plan, grid, st, A, V, ctrl, mode, rowsum_out);          \
+        return;                                                                              \
     }
     WOTB_TC_CASE(16, 4)
     WOTB_TC_CASE(32, 4)
@@ -860,6 +903,8 @@ __global__ void __launch_bounds__(1024) k_mufu_peak(float *out, int iters) {
     for (int e = 0; e < 16; ++e) s += v[e];
     if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
 }
+
+void set_pdl(bool on) { tc_pdl_flag() = on ? 1 : 0; }
 
 int bench_mufu(wotb_ctx *ctx, double *ex2_per_s) {
     WOTB_REQUIRE(ctx && ex2_per_s, "NULL argument");

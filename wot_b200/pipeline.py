@@ -31,6 +31,10 @@ class Pipeline:
             raise ValueError("streams must be >= 1")
         _lib.load().wotb_set_compute_slots(int(compute_slots))
         self._slots = int(compute_slots)
+        self._pdl_off = streams > 1
+        if self._pdl_off:
+            # programmatic dependent launch helps a lone solve and hurts interleaved ones (csrc/online_tc.cuh)
+            _lib.load().wotb_set_pdl(0)
         if device is None:
             device = _lib.context().device
         self.device = int(device)
@@ -75,6 +79,9 @@ class Pipeline:
         self.contexts = []
         if self._slots:
             _lib.load().wotb_set_compute_slots(0)
+        if self._pdl_off:
+            _lib.load().wotb_set_pdl(1)
+            self._pdl_off = False
 
     def __enter__(self):
         return self
