@@ -222,6 +222,19 @@ int wotb_online_state(void *solve, wotb_info *info, int32_t *done);
 int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi);
 void wotb_online_close(void *solve);
 
+/* ---- a coupling applied to populations without materialising it ------------------
+ * Replaces the products of TransportMapModel.push_forward / pull_back, wot/tmap/transport_map_model.py:290
+ * (p @ tmap.X) and :356 (tmap.X @ p.T): the coupling of a finished solve is fully described by the local-PCA
+ * coordinates, the median, the potentials f, g, eps_final and out_scale (wotb_info), so
+ *   forward = 1:  out[k, j] = sum_i p[k, i] tmap[i, j]     p [n_pop, I] -> out [n_pop, J]
+ *   forward = 0:  out[k, i] = sum_j tmap[i, j] p[k, j]     p [n_pop, J] -> out [n_pop, I]
+ * is one pass of the online kernel per population (weights enter as log2 p in the exponent offsets; p >= 0,
+ * as wot.Population measures are).  Host pointers, float64; scale_host as in wotb_transport_map_from_coords_host. */
+int wotb_coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int32_t d,
+                             const double *scale_host, double median, const double *f_host, const double *g_host,
+                             double eps_final, double out_scale, int32_t forward, const double *p_host, int32_t n_pop,
+                             double *out_host);
+
 /* Measurement hook for bench.py: average device time (ms, CUDA events on the context's stream) of one
  * row-pass and one column-pass launch of the stored-K matvec kernels on an I x J kernel matrix. */
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,

@@ -215,7 +215,8 @@ def test_fixed_point_property_large(ot):
     # at a fixed point: a = (p / (K b dy))^alpha1 e^{-u/(l1+eps)}  <=>  r_i / J = p_i exp(-f_i / l1)
     np.testing.assert_allclose(rows / n1, growth * np.exp(-f / l1), rtol=5e-4)
     np.testing.assert_allclose(cols / n0, growth.mean() * np.exp(-g / l2), rtol=5e-4)
-    np.testing.assert_allclose(info["learned_growth"][-1], tmap.sum(axis=1), rtol=1e-6)
+    # growth rows come from the solver's own last pass (default kernel 'auto' -> online: exponent error ~1e-5)
+    np.testing.assert_allclose(info["learned_growth"][-1], tmap.sum(axis=1), rtol=RTOL / 4)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -497,3 +498,54 @@ def test_gpu_pca_vs_sklearn(cells, genes, k):
         want = wot_oracle.compute_default_cost_matrix(p1, p2, np.diag(pca.singular_values_))
         got = wot_oracle.compute_default_cost_matrix(q1, q2, np.diag(gpca.singular_values_))
         np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-11)
+
+
+def test_config0_otmodel_2k_pair_vs_oracle(ot):
+    """BASELINE.json configs[0] at full size: 2 days x 2,000 cells x 1,000 genes through OTModel defaults
+    (local_pca=30, eps=0.05, lambda1=1, lambda2=50, growth_iters=1): GPU PCA -> GPU cost -> GPU solver, against the
+    float64 oracle fed with the reference's own scikit-learn PCA (util.py:240-255)."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    from wot_b200._anndata import AnnData
+    from wot_b200.ot import util
+    X, day, growth = synthetic.expression_matrix([2000, 2000], n_genes=1000, seed=0)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    model = ot.OTModel(AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])])))
+    tm = model.compute_transport_map(0, 1)
+    got_info = ot.last_solve_info()["infos"][0]
+    p0, p1, pca, _ = util.compute_pca_sklearn(X[day == 0], X[day == 1], 30)
+    cost = orc.compute_default_cost_matrix(p0, p1, np.diag(pca.singular_values_))
+    info = orc.SolveInfo()
+    want = orc.optimal_transport_duality_gap(C=cost, G=np.power(growth[day == 0], 1.0), info=info, gap="marginal", **DEFAULTS)
+    assert_coupling_close(np.asarray(tm.X), want)
+    assert abs(got_info["batches"][5] - info.batches[5]) <= 1
+    np.testing.assert_allclose(tm.obs["g1"].values, want.sum(axis=1), rtol=RTOL)
+
+
+def test_implicit_transport_map_push_forward_pull_back(ot):
+    """populations pushed forward / pulled back through a coupling that is never materialised
+    (wot_b200.tmap.ImplicitTransportMap) equal the reference's dense products p @ tmap.X and tmap.X @ p.T
+    (transport_map_model.py:290, :356) on the coupling compute_transport_map returns for the same pair."""
+    from wot_b200 import synthetic
+    from wot_b200._anndata import AnnData
+    X, day, growth = synthetic.expression_matrix([700, 820, 760], n_genes=200, seed=9)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    model = ot.OTModel(AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])])), growth_iters=2,
+                       local_pca=20)
+    dense = model.compute_transport_map(0, 1)
+    imp = model.compute_implicit_transport_map(0, 1)
+    T = np.asarray(dense.X)
+    assert imp.shape == T.shape and list(imp.obs.columns) == ["g0", "g1", "g2"]
+    np.testing.assert_allclose(imp.obs["g2"].values, dense.obs["g2"].values, rtol=RTOL)
+    rng = np.random.default_rng(0)
+    p_rows = np.vstack([np.ones(700) / 700, (rng.random(700) < 0.1).astype(float), rng.random(700)])
+    p_cols = np.vstack([np.ones(820) / 820, (rng.random(820) < 0.05).astype(float)])
+    np.testing.assert_allclose(imp.push_forward(p_rows), p_rows @ T, rtol=RTOL)
+    np.testing.assert_allclose(imp.pull_back(p_cols), (T @ p_cols.T).T, rtol=RTOL)
+    np.testing.assert_allclose(imp.row_sums(), T.sum(axis=1), rtol=RTOL)
+    np.testing.assert_allclose(imp.col_sums(), T.sum(axis=0), rtol=RTOL)
+    # normalised push-forward then pull-back of a cell set, as TransportMapModel.ancestors / descendants chain them
+    q = imp.push_forward(p_rows[1], normalize=True)
+    np.testing.assert_allclose(q, (p_rows[1] @ T) / (p_rows[1] @ T).sum(), rtol=RTOL)
+    with pytest.raises(ValueError):
+        imp.push_forward(-p_rows[0])

@@ -231,6 +231,72 @@ static int finish_host_outputs(wotb_ctx *ctx, int64_t I, int64_t J, const HostVe
     return WOTB_OK;
 }
 
+
+// ---- coupling applied to populations without materialising it ---------------------------------
+// tmap_ij = exp((f_i + g_j - C_ij)/eps) * out_scale  (SURVEY 8 a-note) in base 2 with C_ij = |x_i - y_j|^2 / median:
+//   log2 tmap_ij = [c1 f_i - c2 |x_i|^2] + [c1 g_j - c2 |y_j|^2 + log2 out_scale] + 2 c2 <x_i, y_j>,  c1 = log2(e)/eps, c2 = c1/median
+// off_a belongs to the side that is summed INTO (out), off_b to the side summed OVER (in), which also carries the
+// population weights log2 p.
+__global__ void k_apply_offsets(const double *__restrict__ x_out, int n_out, const double *__restrict__ pot_out,
+                                const double *__restrict__ x_in, int n_in, const double *__restrict__ pot_in,
+                                const double *__restrict__ p_in, int d, double c1, double c2, double log2_scale,
+                                double *__restrict__ off_out, double *__restrict__ off_in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) {
+        double n2 = 0.0;
+        for (int k = 0; k < d; ++k) n2 = fma(x_out[(size_t)i * d + k], x_out[(size_t)i * d + k], n2);
+        off_out[i] = c1 * pot_out[i] - c2 * n2;
+    }
+    if (i < n_in) {
+        double n2 = 0.0;
+        for (int k = 0; k < d; ++k) n2 = fma(x_in[(size_t)i * d + k], x_in[(size_t)i * d + k], n2);
+        const double w = p_in[i];
+        off_in[i] = w > 0.0 ? c1 * pot_in[i] - c2 * n2 + log2_scale + log2(w) : -INFINITY;
+    }
+}
+
+static int coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int d,
+                               const double *scale_host, double median, const double *f_host, const double *g_host,
+                               double eps_final, double out_scale, int forward, const double *p_host, int n_pop,
+                               double *out_host) {
+    WOTB_REQUIRE(ctx && x0_host && x1_host && f_host && g_host && p_host && out_host, "NULL argument");
+    WOTB_REQUIRE(I >= 1 && J >= 1 && d >= 1 && n_pop >= 1 && median > 0 && eps_final > 0 && out_scale > 0, "bad arguments");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n_in = forward ? I : J, n_out = forward ? J : I;
+    const size_t nx0 = (size_t)round_up(I * d, 32) * 8, nx1 = (size_t)round_up(J * d, 32) * 8, nsc = (size_t)round_up(d, 32) * 8;
+    const size_t nI = (size_t)round_up(I, 32) * 8, nJ = (size_t)round_up(J, 32) * 8;
+    const size_t nin = forward ? nI : nJ, nout = forward ? nJ : nI;
+    WOTB_TRY(ctx->hX.reserve(2 * (nx0 + nx1) + nsc + nI + nJ + 2 * nin + 2 * nout + 256));
+    char *b = ctx->hX.as<char>();
+    double *x0 = (double *)b, *x1 = (double *)(b + nx0), *sc = (double *)(b + nx0 + nx1);
+    double *xs0 = (double *)(b + nx0 + nx1 + nsc), *xs1 = (double *)(b + 2 * nx0 + nx1 + nsc);
+    char *v = b + 2 * (nx0 + nx1) + nsc;
+    double *f = (double *)v, *g = (double *)(v + nI), *p = (double *)(v + nI + nJ), *off_in = (double *)(v + nI + nJ + nin);
+    double *off_out = (double *)(v + nI + nJ + 2 * nin), *sums = (double *)(v + nI + nJ + 2 * nin + nout);
+    WOTB_CUDA(cudaMemcpyAsync(x0, x0_host, (size_t)I * d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(x1, x1_host, (size_t)J * d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(f, f_host, (size_t)I * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(g, g_host, (size_t)J * 8, cudaMemcpyHostToDevice, st));
+    if (scale_host) WOTB_CUDA(cudaMemcpyAsync(sc, scale_host, (size_t)d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_TRY(scale_into(ctx, x0, I, d, scale_host ? sc : nullptr, xs0));
+    WOTB_TRY(scale_into(ctx, x1, J, d, scale_host ? sc : nullptr, xs1));
+    const double c1 = 1.4426950408889634 / eps_final, c2 = c1 / median;
+    const double *x_out = forward ? xs1 : xs0, *x_in = forward ? xs0 : xs1;
+    const double *pot_out = forward ? g : f, *pot_in = forward ? f : g;
+    const int impl = d <= 46 ? 2 : 0;  // tcgen05 pass when the coordinates fit its K budget, SIMT FP32 otherwise
+    for (int k = 0; k < n_pop; ++k) {
+        WOTB_CUDA(cudaMemcpyAsync(p, p_host + (size_t)k * n_in, (size_t)n_in * 8, cudaMemcpyHostToDevice, st));
+        const int64_t n = n_in > n_out ? n_in : n_out;
+        k_apply_offsets<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(x_out, (int)n_out, pot_out, x_in, (int)n_in, pot_in, p, d, c1, c2,
+                                                                 log2(out_scale), off_out, off_in);
+        WOTB_TRY(online_rowsums(ctx, x_out, n_out, x_in, n_in, d, sqrt(2.0 * c2), off_out, off_in, impl, 0, sums, nullptr));
+        WOTB_CUDA(cudaMemcpyAsync(out_host + (size_t)k * n_out, sums, (size_t)n_out * 8, cudaMemcpyDeviceToHost, st));
+    }
+    WOTB_CUDA(cudaStreamSynchronize(st));
+    return WOTB_OK;
+}
+
 }  // namespace wotb
 
 using namespace wotb;
@@ -538,6 +604,14 @@ int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, c
 }
 
 int wotb_bench_mufu_dev(wotb_ctx *ctx, double *ex2_per_s) { return bench_mufu(ctx, ex2_per_s); }
+
+int wotb_coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int32_t d,
+                             const double *scale_host, double median, const double *f_host, const double *g_host,
+                             double eps_final, double out_scale, int32_t forward, const double *p_host, int32_t n_pop,
+                             double *out_host) {
+    return coupling_apply_host(ctx, x0_host, I, x1_host, J, d, scale_host, median, f_host, g_host, eps_final, out_scale,
+                               forward, p_host, n_pop, out_host);
+}
 
 int wotb_pinned_alloc(size_t bytes, void **out) {
     WOTB_REQUIRE(out != nullptr, "out is NULL");

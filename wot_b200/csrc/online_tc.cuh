@@ -758,7 +758,7 @@ __global__ void k_pad_offsets(const double *__restrict__ src, int n, double *__r
 int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const double *x_in, int64_t n_in, int d, double scale,
                    const double *off_out, const double *off_in, int impl, int reps, double *sums, double *ms_per_pass) {
     WOTB_REQUIRE(ctx && x_out && x_in && off_out && off_in && sums, "NULL argument");
-    WOTB_REQUIRE(n_out >= 1 && n_in >= 1 && d >= 1 && reps >= 1, "bad sizes");
+    WOTB_REQUIRE(n_out >= 1 && n_in >= 1 && d >= 1 && reps >= 0, "bad sizes");
     const int dbg = impl >> 4;
     impl &= 15;
     WOTB_REQUIRE(impl == 0 || ((impl == 1 || impl == 2) && tc_supported(d)),

@@ -209,6 +209,23 @@ class OTModel:
         config = {**self.ot_config, **local_config, "t0": t0, "t1": t1, "covariate": covariate, "C": cost_matrix}
         return self.compute_single_transport_map(config)
 
+    def compute_implicit_transport_map(self, t0, t1, covariate=None):
+        """Additive (not in the reference): the transport map from t0 to t1 WITHOUT its I x J matrix, as a
+        wot_b200.tmap.ImplicitTransportMap (coordinates, potentials, epsilon) that pushes populations forward and
+        pulls them back on the GPU (the products of transport_map_model.py:290, :356).  `obs` carries the same
+        g0..gN growth columns as compute_transport_map's result."""
+        if self.day_pairs is not None:
+            if (t0, t1) not in self.day_pairs:
+                raise ValueError("Transport map ({},{}) is not present in day_pairs".format(t0, t1))
+            local_config = self.day_pairs[(t0, t1)]
+        else:
+            local_config = {}
+        if self.solver not in (_ot.optimal_transport_duality_gap, _ot.transport_stablev2):
+            raise ValueError("implicit transport maps need one of the built-in solvers")
+        config = {**self.ot_config, **local_config, "t0": t0, "t1": t1, "covariate": covariate, "C": None,
+                  "implicit": True}
+        return self.compute_single_transport_map(config)
+
     @staticmethod
     def compute_default_cost_matrix(a, b, eigenvals=None):
         """Median-normalised squared Euclidean cost (ot_model.py:242-253), computed on the GPU."""
@@ -259,6 +276,22 @@ class OTModel:
             config["G"] = np.ones(p0.shape[0])
 
         ours = self.solver in (_ot.optimal_transport_duality_gap, _ot.transport_stablev2)
+        if config.pop("implicit", False):
+            from ..tmap import ImplicitTransportMap
+            solver_id = _ot._SOLVER_IDS[self.solver]
+            growth_iters = int(config["growth_iters"])
+            keys = ("lambda1", "lambda2", "epsilon", "batch_size", "tolerance", "tau", "epsilon0", "max_iter",
+                    "scaling_iter", "extra_iter", "inner_iter_max")
+            _, learned = _ot.solve_coords(p0_x, p1_x, config["G"], solver_id, scale=scale, growth_iters=growth_iters,
+                                          kernel=config.get("kernel", "auto"), want_tmap=False,
+                                          **{k: config[k] for k in keys if k in config})
+            last = _ot.last_solve_info()
+            info = last["infos"][-1]
+            obs_growth = {"g" + str(k): np.power(learned[k], 1.0 / delta_days) for k in range(growth_iters + 1)}
+            return ImplicitTransportMap(p0_x, p1_x, last["f"], last["g"], last["median"], info["eps_final"],
+                                        info["out_scale"], scale=scale,
+                                        obs=pd.DataFrame(index=p0.obs.index, data=obs_growth),
+                                        var=pd.DataFrame(index=p1.obs.index), t0=t0, t1=t1)
         if config["C"] is None and ours:
             # default cost, growth loop and final row sums in one library call; C never visits the host
             config["coords"] = (p0_x, p1_x, scale)
