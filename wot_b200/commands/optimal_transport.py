@@ -2,7 +2,8 @@
 
 Flags, defaults and their mapping onto OTModel keywords follow the reference verbatim
 (wot/commands/util.py:179-237 and :146-176; wot/commands/optimal_transport.py:12-30).  Additive flags:
---kernel {stored,online}, and --format also accepts txt / npz (usable without anndata / h5py).
+--kernel {auto,stored,online}, --streams N (day-pairs in flight per GPU), and --format also accepts txt / npz
+(usable without anndata / h5py).
 Run one process per GPU under torchrun to shard the day-pairs across GPUs.
 """
 from __future__ import annotations
@@ -56,6 +57,8 @@ def add_ot_parameters_arguments(parser):
 def initialize_ot_model_from_args(args):
     from .. import ot
     extra = {"kernel": args.kernel} if getattr(args, "kernel", None) else {}
+    if getattr(args, "streams", None):
+        extra["streams"] = args.streams
     return ot.initialize_ot_model(
         args.matrix, cell_days=args.cell_days, solver=args.solver, local_pca=args.local_pca,
         growth_rate_field=args.growth_rate_field, day_field=args.day_field,
@@ -76,8 +79,11 @@ def create_parser():
     parser.add_argument("--no_overwrite", action="store_true",
                         help="Do not overwrite existing transport maps if they exist")
     parser.add_argument("--out", default="./tmaps", help="Prefix for output file names")
-    parser.add_argument("--kernel", choices=["stored", "online"], default=None,
-                        help="GPU kernel family: K kept in HBM (default) or recomputed from coordinates")
+    parser.add_argument("--kernel", choices=["auto", "stored", "online"], default=None,
+                        help="GPU kernel family: K kept in HBM, or recomputed from coordinates on tcgen05 + MUFU "
+                             "(default auto: online unless the final epsilon is below 0.02 or local_pca > 46)")
+    parser.add_argument("--streams", type=int, default=None,
+                        help="Day-pairs kept in flight per GPU on separate CUDA streams (default 2; 1 = serial loop)")
     return parser
 
 
