@@ -467,6 +467,8 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_steps / t_e2e
     pipe2.close()
     del outs
+    if n_streams > 1:
+        ctx.lib.wotb_set_pdl(0)      # pipe2.close() restored the default; `pipe` (several streams) is still open
 
     if rank != 0:
         if dist is not None:

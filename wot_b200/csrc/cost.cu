@@ -11,6 +11,9 @@
 // Also here: the coupling materialisation exp((f_i + g_j - C_ij)/eps)/J (optimal_transport.py:153,164).
 #include <math.h>
 
+#include <stddef.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace wotb {
@@ -124,6 +127,7 @@ struct SelectState {
     unsigned long long n_bucket;   // elements inside the prefix bucket
     unsigned long long min_above;  // bit pattern of the smallest value above the selected one
     int pass;
+    int use_flat;                  // set by k_select_pick after the second digit when the bucket fits the gather buffer
 };
 
 __host__ __device__ inline int sel_shift(int pass) { return pass == 0 ? 55 : 55 - 11 * pass; }
@@ -150,6 +154,7 @@ struct SelectSink {
 __global__ void __launch_bounds__(kTileThreads) k_select_hist(const double *x0, long long I, const double *x1,
                                                               long long J, int d, SelectState *st) {
     __shared__ unsigned int hist[kSelBins];
+    if (st->use_flat) return;  // the remaining digits are found on the gathered bucket (k_flat_hist)
     for (int b = threadIdx.x; b < kSelBins; b += kTileThreads) hist[b] = 0;
     __syncthreads();
     SelectSink sink{hist, st->prefix, st->pass};
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(kTileThreads) k_select_hist(const double *x0, 
         if (hist[b]) atomicAdd(&st->hist[b], (unsigned long long)hist[b]);
 }
 
-__global__ void k_select_pick(SelectState *st) {
+__global__ void k_select_pick(SelectState *st, unsigned int flat_cap) {
     if (threadIdx.x != 0) return;
     const int bits = sel_bits(st->pass);
     unsigned long long below = 0, rank = st->rank;
@@ -177,6 +182,7 @@ __global__ void k_select_pick(SelectState *st) {
     st->rank = rank - below;
     st->n_less += below;
     st->pass += 1;
+    if (st->pass == 2 && flat_cap > 0 && st->n_bucket <= (unsigned long long)flat_cap) st->use_flat = 1;
     for (int b = 0; b < kSelBins; ++b) st->hist[b] = 0;
 }
 
@@ -204,6 +210,82 @@ __global__ void __launch_bounds__(kTileThreads) k_select_min_above(const double 
     }
     if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&st->min_above, best);
 }
+
+// ---- shortcut: once the prefix bucket is small, gather it and finish the select on the flat buffer ----------
+// After the 9- and 11-bit passes the bucket that holds the median is a sliver of one binade (~0.2 % of the I*J
+// values at atlas shapes): one more pass over the tiles appends its members to a buffer, and the remaining four
+// digits (and the upper middle element for even counts) are found there, instead of four more FP64 passes over
+// all I*J distances.  Same values, same order statistics: the result is still the exact np.median.
+struct CollectSink {
+    unsigned long long *buf;
+    unsigned int *count;
+    unsigned long long prefix;
+    unsigned int cap;
+    int shift;  // bits below the prefix
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[c]);
+            const bool in = i < I && j + c < J && (key >> shift) == prefix;
+            const unsigned int mask = __ballot_sync(0xffffffffu, in);
+            if (mask) {
+                const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const unsigned int at = base + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+                if (in && at < cap) buf[at] = key;
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(kTileThreads) k_select_collect(const double *x0, long long I, const double *x1,
+                                                                 long long J, int d, const SelectState *st,
+                                                                 unsigned long long *buf, unsigned int *count,
+                                                                 unsigned int cap) {
+    if (!st->use_flat) return;
+    CollectSink sink{buf, count, st->prefix, cap, sel_shift(st->pass - 1)};
+    dist_tiles(x0, I, x1, J, d, sink);
+}
+
+__global__ void k_flat_hist(const unsigned long long *__restrict__ buf, const unsigned int *__restrict__ count,
+                            SelectState *st) {
+    __shared__ unsigned int hist[kSelBins];
+    if (!st->use_flat) return;
+    const unsigned int n = *count;
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const int pass = st->pass, shift = sel_shift(pass), bits = sel_bits(pass);
+    const unsigned long long prefix = st->prefix;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned long long key = buf[e];
+        if ((key >> (shift + bits)) == prefix) atomicAdd(&hist[(unsigned int)((key >> shift) & ((1u << bits) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        if (hist[b]) atomicAdd(&st->hist[b], (unsigned long long)hist[b]);
+}
+
+__global__ void k_flat_min_above(const unsigned long long *__restrict__ buf, const unsigned int *__restrict__ count,
+                                 SelectState *st) {
+    if (!st->use_flat) return;
+    const unsigned int n = *count;
+    const unsigned long long key1 = st->prefix;
+    unsigned long long best = ~0ull;
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned long long key = buf[e];
+        if (key > key1 && key < best) best = key;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&st->min_above, best);
+}
+
+constexpr unsigned int kSelCollectCap = 1u << 22;  // 4 M keys = 32 MB
 
 static int tile_grid(const wotb_ctx *ctx, int64_t I, int64_t J) {
     const int64_t tiles = cdiv(I, kTile) * cdiv(J, kTile);
@@ -252,21 +334,49 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     init.min_above = ~0ull;
     WOTB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     const int grid = tile_grid(ctx, I, J);
+    // One launch sequence, no host decision inside it: after the second digit k_select_pick sets use_flat on the
+    // device when the bucket fits the gather buffer; from then on the tile-pass kernels return at once and the
+    // flat kernels do the work (or the other way round).  The scalar tail of SelectState comes back through
+    // pinned memory.
+    const bool shortcut = getenv("WOTB_NO_MEDIAN_SHORTCUT") == nullptr;
+    WOTB_TRY(ctx->status.reserve(256));
+    struct Tail {
+        unsigned long long prefix, rank, n_less, n_bucket, min_above;
+        int pass, use_flat;
+    };
+    static_assert(offsetof(SelectState, use_flat) - offsetof(SelectState, prefix) == offsetof(Tail, use_flat), "SelectState tail layout");
+    Tail *pin = reinterpret_cast<Tail *>(ctx->status.as<char>() + 64);
+    auto read_tail = [&](Tail *out) -> int {
+        WOTB_CUDA(cudaMemcpyAsync(pin, &st->prefix, sizeof(Tail), cudaMemcpyDeviceToHost, ctx->stream));
+        WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = *pin;
+        return WOTB_OK;
+    };
+    // always the full cap: a grow-only buffer that never has to be re-allocated mid-run (cudaFree is a device-wide
+    // synchronisation, which would stall the other streams of a pipeline)
+    WOTB_TRY(ctx->part.reserve((size_t)kSelCollectCap * 8 + 256));
+    unsigned long long *buf = ctx->part.as<unsigned long long>() + 32;
+    unsigned int *count = ctx->part.as<unsigned int>();
+    WOTB_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
+    const unsigned int flat_cap = shortcut ? kSelCollectCap : 0u;
     for (int pass = 0; pass < 6; ++pass) {
+        if (pass == 2) k_select_collect<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st, buf, count, kSelCollectCap);
+        if (pass >= 2) k_flat_hist<<<592, 256, 0, ctx->stream>>>(buf, count, st);
         k_select_hist<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
-        k_select_pick<<<1, 32, 0, ctx->stream>>>(st);
+        k_select_pick<<<1, 32, 0, ctx->stream>>>(st, flat_cap);
     }
-    SelectState fin;
-    WOTB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
-    WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n % 2 == 0) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
+    Tail fin;
+    WOTB_TRY(read_tail(&fin));
     double lo, hi;
     memcpy(&lo, &fin.prefix, 8);
     hi = lo;
     if (n % 2 == 0 && fin.n_less + fin.n_bucket <= n / 2) {
-        // the upper middle element is the smallest value strictly above `lo`
-        k_select_min_above<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
-        WOTB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
-        WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+        // the upper middle element is the smallest value strictly above `lo`: the gathered bucket usually has it
+        if (!(fin.use_flat && fin.min_above != ~0ull)) {  // `lo` is the largest member of its bucket (or no bucket)
+            k_select_min_above<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
+            WOTB_TRY(read_tail(&fin));
+        }
         memcpy(&hi, &fin.min_above, 8);
     }
     WOTB_CUDA(cudaGetLastError());
