@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every day by this factor (debugging)")
     ap.add_argument("--kernel", default="online", choices=["stored", "online", "online_simt"])
-    ap.add_argument("--cpu-cells", type=int, default=2200, help="cells/day of the bounded CPU sample")
+    ap.add_argument("--cpu-cells", type=int, default=3200, help="cells/day of the bounded CPU sample (~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=None,
                     help="day-pairs in flight per GPU, each on its own CUDA stream (wot_b200.pipeline)")
