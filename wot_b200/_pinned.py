@@ -1,11 +1,14 @@
 """Pool of page-locked host blocks for coupling outputs.
 
-cudaHostAlloc costs ~0.3 ms per MiB, comparable to solving the day-pair whose coupling it holds, so blocks
-are recycled: when the last ndarray viewing a block is garbage-collected the block returns to the pool and
-the next transport map of similar size reuses it (compute_all_transport_maps drops each map after writing it).
+cudaHostAlloc costs ~0.3 ms per MiB (350 ms for the 1.2 GB coupling of a mean atlas pair, more than solving the
+pair) and synchronises the device, so blocks are recycled: when the last ndarray viewing a block is
+garbage-collected the block returns to the pool (compute_all_transport_maps drops each map after writing it).
+Day-pairs differ in size by up to 16x, so a new block is never smaller than the largest one handed out so far:
+after the first few maps every idle block fits every request and the pool stops allocating.
 """
 from __future__ import annotations
 
+import threading
 import weakref
 
 import numpy as np
@@ -13,7 +16,10 @@ import numpy as np
 from . import _lib
 
 _free = []          # PinnedArray blocks nobody views
-_MAX_IDLE = 3
+_lock = threading.Lock()
+_MAX_IDLE = 4
+_largest = 0        # bytes of the largest block allocated so far
+_GRANULE = 64 << 20
 
 
 class _PinnedNd(np.ndarray):
@@ -22,17 +28,27 @@ class _PinnedNd(np.ndarray):
 
 
 def _give_back(block):
-    if len(_free) < _MAX_IDLE:
-        _free.append(block)
+    with _lock:
+        if len(_free) < _MAX_IDLE:
+            _free.append(block)
 
 
 def empty(shape, dtype):
+    global _largest
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    best = None
-    for k, blk in enumerate(_free):
-        if blk.nbytes >= nbytes and blk.nbytes <= 2 * nbytes + (1 << 20) and (best is None or blk.nbytes < _free[best].nbytes):
-            best = k
-    block = _free.pop(best) if best is not None else _lib.PinnedArray(max(nbytes, 1))
+    with _lock:
+        best = None
+        for k, blk in enumerate(_free):
+            if blk.nbytes >= nbytes and (best is None or blk.nbytes < _free[best].nbytes):
+                best = k
+        block = _free.pop(best) if best is not None else None
+        if block is None:
+            want = max(nbytes, 1)
+            if want >= _GRANULE:                      # large outputs: size for the largest request seen so far
+                want = max(-(-want // _GRANULE) * _GRANULE, _largest)
+                _largest = want
+    if block is None:
+        block = _lib.PinnedArray(want)
     arr = block.view(shape, dtype).view(_PinnedNd)
     arr._block = block
     weakref.finalize(arr, _give_back, block)
@@ -40,4 +56,7 @@ def empty(shape, dtype):
 
 
 def drain():
-    _free.clear()
+    global _largest
+    with _lock:
+        _free.clear()
+        _largest = 0

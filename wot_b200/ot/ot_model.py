@@ -29,6 +29,15 @@ _DEFAULTS = {"local_pca": 30, "growth_iters": 1, "epsilon": 0.05, "lambda1": 1, 
              "batch_size": 5, "extra_iter": 1000}  # ot_model.py:85-87
 
 
+def _rows_key(mask):
+    """A boolean row mask as a slice when the selected rows are one contiguous run (matrices sorted by day): the
+    day's expression rows are then a view, not a 150 MB copy."""
+    idx = np.flatnonzero(mask)
+    if len(idx) > 0 and idx[-1] - idx[0] + 1 == len(idx):
+        return slice(int(idx[0]), int(idx[-1]) + 1)
+    return mask
+
+
 def _dense(x):
     return x.toarray() if scipy.sparse.isspmatrix(x) else np.asarray(x)
 
@@ -181,9 +190,10 @@ class OTModel:
             # next pairs runs on the host meanwhile.  Files and the row order of '{prefix}_g.txt' are those of
             # the serial loop.
             from ..pipeline import Pipeline
+            counts = self.matrix.obs[self.day_field].value_counts()
+            costs = [float(counts.get(job[0][0], 0)) * float(counts.get(job[0][1], 0)) for job in todo]
             with Pipeline(streams=self.streams + 1, compute_slots=self.streams) as pipe:
-                futures = [pipe.submit(lambda ctx, job=job: one(*job)) for job in todo]
-                frames = [f.result() for f in futures]
+                frames = pipe.map(lambda ctx, job: one(*job), todo, costs=costs)
         else:
             frames = [one(*job) for job in todo]
         growth_frames = [f for f in frames if f is not None]
@@ -252,8 +262,8 @@ class OTModel:
         if covariate is not None:
             sel0 = sel0 & (ds.obs[self.covariate_field] == covariate[0]).values
             sel1 = sel1 & (ds.obs[self.covariate_field] == covariate[1]).values
-        p0 = ds[sel0, :]
-        p1 = ds[sel1, :]
+        p0 = ds[_rows_key(sel0), :]
+        p1 = ds[_rows_key(sel1), :]
         if p0.shape[0] == 0:
             logger.info("No cells at {}".format(t0))
             return None

@@ -92,7 +92,8 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
         # this rank's pairs, `streams` solves in flight on its GPU plus one coupling on its way to the host
         from .pipeline import Pipeline
         with Pipeline(device=int(os.environ.get("LOCAL_RANK", "0")), streams=streams + 1, compute_slots=streams) as pipe:
-            got = pipe.map(lambda ctx, k: one(k), mine)
+            cost_of = dict(zip(todo, costs))
+            got = pipe.map(lambda ctx, k: one(k), mine, costs=[cost_of[k] for k in mine])
     else:
         got = [one(k) for k in mine]
     for k, obs in zip(mine, got):

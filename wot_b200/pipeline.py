@@ -20,6 +20,12 @@ from concurrent.futures import Future
 from . import _lib
 
 
+# Library contexts are kept between pipelines: their grow-only workspaces are sized by the largest day-pair seen,
+# and growing one (cudaFree + cudaMalloc) synchronises the whole device, i.e. stalls every stream of a pipeline.
+_idle_contexts = {}      # device -> [Context]
+_idle_lock = threading.Lock()
+
+
 class Pipeline:
     def __init__(self, device=None, streams=2, make_stream=None, compute_slots=0):
         """`make_stream(k)` may return a raw cudaStream_t handle for context k (e.g. a torch stream's
@@ -38,7 +44,15 @@ class Pipeline:
         if device is None:
             device = _lib.context().device
         self.device = int(device)
-        self.contexts = [_lib.Context(self.device, make_stream(k) if make_stream else None) for k in range(streams)]
+        self._cached = make_stream is None        # contexts on caller-owned streams die with the pipeline
+        self.contexts = []
+        for k in range(streams):
+            ctx = None
+            if self._cached:
+                with _idle_lock:
+                    idle = _idle_contexts.get(self.device, [])
+                    ctx = idle.pop() if idle else None
+            self.contexts.append(ctx or _lib.Context(self.device, make_stream(k) if make_stream else None))
         self._jobs = queue.Queue()
         self._threads = [threading.Thread(target=self._work, args=(ctx,), daemon=True) for ctx in self.contexts]
         for t in self._threads:
@@ -64,10 +78,14 @@ class Pipeline:
         self._jobs.put((fut, fn, args, kwargs))
         return fut
 
-    def map(self, fn, items):
-        """fn(ctx, item) for every item, at most `streams` at a time; results in the order of `items`."""
-        futs = [self.submit(fn, item) for item in items]
-        return [f.result() for f in futs]
+    def map(self, fn, items, costs=None):
+        """fn(ctx, item) for every item, at most `streams` at a time; results in the order of `items`.
+        With `costs`, items are started largest first (the first jobs size every context's workspaces once, and
+        the tail of the run is made of short jobs)."""
+        order = range(len(items)) if costs is None else sorted(range(len(items)), key=lambda k: (-costs[k], k))
+        futs = {k: self.submit(fn, items[k]) for k in order}
+        return [futs[k].result() for k in range(len(items))]
+
 
     def close(self):
         for _ in self._threads:
@@ -75,7 +93,11 @@ class Pipeline:
         for t in self._threads:
             t.join()
         for ctx in self.contexts:
-            ctx.close()
+            if self._cached:
+                with _idle_lock:
+                    _idle_contexts.setdefault(self.device, []).append(ctx)
+            else:
+                ctx.close()
         self.contexts = []
         if self._slots:
             _lib.load().wotb_set_compute_slots(0)
@@ -88,3 +110,12 @@ class Pipeline:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def release_idle_contexts():
+    """Destroy the cached contexts (frees their device workspaces)."""
+    with _idle_lock:
+        for ctxs in _idle_contexts.values():
+            for ctx in ctxs:
+                ctx.close()
+        _idle_contexts.clear()
