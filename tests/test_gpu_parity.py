@@ -417,6 +417,10 @@ def test_parameter_sweep_driver_single_gpu(ot):
     common = {k: v for k, v in DEFAULTS.items() if k not in ("epsilon", "lambda1", "lambda2", "growth_iters")}
     res = parallel.parameter_sweep(x0, x1, growth, grid, kernel="online", **common)
     assert [r["setting"] for r in res] == grid
+    res2 = parallel.parameter_sweep(x0, x1, growth, grid, kernel="online", streams=2, **common)   # two in flight
+    for a, b in zip(res, res2):
+        assert a["setting"] == b["setting"] and a["iters"] == b["iters"] and a["batches"] == b["batches"]
+        np.testing.assert_array_equal(a["rowsum"], b["rowsum"])
     for r in res:
         tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
                                               G=growth.copy(), kernel="online", **dict(DEFAULTS, **r["setting"]))

@@ -2,7 +2,7 @@
 """BASELINE.json configs[4]: the 64-setting (epsilon, lambda1, lambda2) sweep on one 10k x 10k day-pair, settings
 dealt to the GPUs through a dynamic queue (wot_b200.parallel.parameter_sweep).  Launch with torchrun for N > 1.
 
-  python tools/sweep.py [cells] [kernel]      kernel: auto (default) | online | stored
+  python tools/sweep.py [cells] [kernel] [streams]      kernel: auto (default) | online | stored; streams per GPU (default 2)
 
 Rank 0 prints one JSON line: wall seconds for the whole sweep, settings/s, total Sinkhorn iterations/s."""
 import json
@@ -20,6 +20,7 @@ def main():
 
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
     kernel = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    streams = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
@@ -33,14 +34,14 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = parallel.parameter_sweep(x0, x1, growth, grid, kernel=kernel, **common)
+    res = parallel.parameter_sweep(x0, x1, growth, grid, kernel=kernel, streams=streams, **common)
     wall = time.perf_counter() - t0
     if rank == 0:
         iters = sum(r["iters"] for r in res)
         per_rank = [sum(1 for r in res if r["rank"] == k) for k in range(world)]
         print(json.dumps({
             "config": "validation-sweep-shaped: 64 (eps, lambda1, lambda2) settings x %dx%d pair, kernel=%s" % (n, n, kernel),
-            "n_gpus": world, "wall_s": wall, "settings_per_s": len(grid) / wall, "sinkhorn_iters": iters,
+            "n_gpus": world, "streams_per_gpu": streams, "wall_s": wall, "settings_per_s": len(grid) / wall, "sinkhorn_iters": iters,
             "sinkhorn_iters_per_s": iters / wall, "settings_per_rank": per_rank,
             "iters_min_max": [min(r["iters"] for r in res), max(r["iters"] for r in res)],
             "not_converged": [r["setting"] for r in res if r["status"] != 0],

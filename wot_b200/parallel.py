@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -164,17 +165,21 @@ def expected_sweep_cost(setting):
 
 
 def parameter_sweep(x0, x1, G, settings, solve=None, group=None, store=None, queue_key="wot_b200/sweep",
-                    growth_iters=1, kernel="online", **common):
+                    growth_iters=1, kernel="online", streams=1, **common):
     """BASELINE.json configs[4]: many (epsilon, lambda1, lambda2) settings on ONE day-pair, settings dealt to
     the ranks through a dynamic queue (independent units; no data-path collective).
 
     `solve(x0, x1, G, **params) -> dict` runs one setting; the default runs the GPU growth loop from
     coordinates without materialising the coupling and reports iteration/batch counts, the duality gap,
     the final row sums and the potentials.  Returns, on every rank, the list of per-setting results in the
-    order of `settings` (each tagged with the rank that ran it)."""
+    order of `settings` (each tagged with the rank that ran it).  `streams` > 1 (GPU solves only): every rank keeps
+    that many settings in flight on separate CUDA streams (wot_b200.pipeline), each worker drawing from the same
+    queue."""
     rank, world = _rank_world(group)
     if solve is None:
         solve = _sweep_solve_gpu
+    else:
+        streams = 1
     order = sorted(range(len(settings)), key=lambda k: (-expected_sweep_cost(settings[k]), k))
     mine = {}
     global _sweep_calls
@@ -183,13 +188,32 @@ def parameter_sweep(x0, x1, G, settings, solve=None, group=None, store=None, que
     if world > 1:
         import torch.distributed as dist
         dist.barrier(group=group)      # start drawing together
-    for k in WorkQueue(order, store=store, key=queue_key):
-        params = dict(common)
-        params.update(settings[k])
-        res = solve(x0, x1, G, growth_iters=growth_iters, kernel=kernel, **params)
-        res["rank"] = rank
-        res["setting"] = dict(settings[k])
-        mine[k] = res
+    queue = WorkQueue(order, store=store, key=queue_key)
+    queue_lock = threading.Lock()
+
+    def draw():
+        with queue_lock:                      # one store round trip at a time per rank
+            return next(queue, None)
+
+    def work(ctx=None):
+        while True:
+            k = draw()
+            if k is None:
+                return
+            params = dict(common)
+            params.update(settings[k])
+            res = solve(x0, x1, G, growth_iters=growth_iters, kernel=kernel, **params)
+            res["rank"] = rank
+            res["setting"] = dict(settings[k])
+            mine[k] = res
+
+    if streams > 1:
+        from .pipeline import Pipeline
+        with Pipeline(device=int(os.environ.get("LOCAL_RANK", "0")), streams=streams) as pipe:
+            for fut in [pipe.submit(work) for _ in range(streams)]:
+                fut.result()
+    else:
+        work()
     parts = [mine]
     if world > 1:
         import torch.distributed as dist
@@ -204,7 +228,7 @@ def parameter_sweep(x0, x1, G, settings, solve=None, group=None, store=None, que
 def _sweep_solve_gpu(x0, x1, G, growth_iters=1, kernel="online", **params):
     from . import _lib
     from .ot import optimal_transport as wot_ot
-    device = int(os.environ.get("LOCAL_RANK", "0"))
+    device = int(os.environ.get("LOCAL_RANK", "0"))      # a pipeline worker's bound context takes precedence
     _, learned = wot_ot.solve_coords(x0, x1, G, _lib.SOLVER_DUALITY_GAP, growth_iters=growth_iters, kernel=kernel,
                                      want_tmap=False, device=device, **params)
     last = wot_ot.last_solve_info()
