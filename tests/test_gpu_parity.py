@@ -553,3 +553,26 @@ def test_implicit_transport_map_push_forward_pull_back(ot):
     np.testing.assert_allclose(q, (p_rows[1] @ T) / (p_rows[1] @ T).sum(), rtol=RTOL)
     with pytest.raises(ValueError):
         imp.push_forward(-p_rows[0])
+
+
+@pytest.mark.parametrize("kernel", ["stored", "online", "online_simt"])
+@pytest.mark.parametrize("shape,d", [((1, 1), 3), ((1, 7), 2), ((6, 1), 4), ((2, 3), 1), ((5, 300), 30), ((257, 3), 30),
+                                     ((33, 65), 46), ((40, 50), 47)])
+def test_tiny_and_ragged_shapes_vs_oracle(ot, shape, d, kernel):
+    """Edge shapes: single cells on either side, fewer cells than one tile, one coordinate, the largest d the
+    tcgen05 pass takes (46) and the first one it hands to the SIMT pass (47)."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    n0, n1 = shape
+    x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=d, seed=17 + n0 + n1)
+    if n0 * n1 == 1:
+        x1 = x1 + 1.0       # a single pair at distance 0 has median 0 (the reference divides by it, too)
+    info = orc.SolveInfo()
+    want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
+                                             gap="marginal", **DEFAULTS)
+    tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
+                                          G=growth.copy(), kernel=kernel, **DEFAULTS)
+    assert tmap.shape == want.shape
+    assert_coupling_close(tmap, want)
+    got = ot.last_solve_info()
+    assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
