@@ -576,3 +576,21 @@ def test_tiny_and_ragged_shapes_vs_oracle(ot, shape, d, kernel):
     assert_coupling_close(tmap, want)
     got = ot.last_solve_info()
     assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+
+
+def test_nan_gap_raises_like_the_reference(ot):
+    """optimal_transport.py:162-163: a NaN duality gap raises RuntimeError("Overflow encountered in duality gap
+    computation, ...").  A caller-supplied cost 1e4 times the normalised one underflows every K entry in the reference
+    (float64) and here (fp32 K) alike."""
+    import warnings
+    from oracle import wot_oracle as orc
+    C, G = pair_cost(60, 70, 3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(RuntimeError, match="Overflow encountered in duality gap computation"):
+            orc.optimal_transport_duality_gap(C=C * 1e4, G=G, info=orc.SolveInfo(), **DEFAULTS)
+    with pytest.raises(RuntimeError, match="Overflow encountered in duality gap computation"):
+        _solve(ot, "optimal_transport_duality_gap", C * 1e4, G)
+    # the context stays usable after the error
+    tmap, _ = _solve(ot, "optimal_transport_duality_gap", C, G)
+    assert np.isfinite(tmap).all()
