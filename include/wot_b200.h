@@ -200,11 +200,13 @@ int wotb_default_cost_matrix_host(wotb_ctx *ctx, const double *x0_host, int64_t 
 /* ---- row-sharded online solve: one huge day-pair across GPUs (BASELINE.json configs[3]) ----------
  * One process per GPU; every rank calls the same sequence.  x0, x1, G are the FULL arrays on every rank
  * (device, float64); rank `shard` of `n_shards` computes a contiguous slice of 128-row tiles.  The solver
- * state is replicated; two float64 vectors per iteration are summed across ranks by the CALLER (NCCL
- * all-reduce on the context's stream) between the steps, through `exchange` (device, max(I,J) doubles):
+ * state is replicated; one float64 vector per iteration is summed across ranks by the CALLER (NCCL
+ * all-reduce on the context's stream) between the steps, through `exchange` (device, 2 I + J doubles):
  *
  *   per batch:      step BEGIN_A, all-reduce exchange[0:I], step BEGIN_B
- *   per iteration:  step ROW, all-reduce exchange[0:I], step COL_PARTIAL, all-reduce exchange[0:J], step COL_FINISH
+ *   per iteration:  step ROW, step COL_PARTIAL, all-reduce exchange[0 : 2I + J], step COL_FINISH
+ *                   (one exchange: gathered a | their row sums | partial column sums; the column pass over a
+ *                   rank's own rows needs only that rank's a)
  *   per batch end:  step GAP_ROWS, all-reduce exchange[0:I], step CHECK, then wotb_online_state() (syncs)
  *   when done:      step FINAL_ROWS, all-reduce exchange[0:I]  -> row sums of the coupling
  *

@@ -256,9 +256,10 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
 //
 // Every rank holds all coordinates (O((I+J) d), a few MB) and the full O(I+J) solver state, replicated;
 // it computes the row half-step for its slice of row tiles and the partial column sums over the same
-// slice.  Two exchanges per iteration, both a SUM all-reduce of one float64 vector (the caller runs them
-// with NCCL on the context's stream): the a-slices (zeros outside the slice, so the sum is an exact
-// all-gather) and the partial column sums.  Because the state is replicated, the convergence checks and
+// slice.  ONE exchange per iteration, a SUM all-reduce of one float64 vector of 2 I + J entries (the caller
+// runs it with NCCL on the context's stream): the a-slices and their row sums (zeros outside the slice, so the
+// sum is an exact all-gather) followed by the partial column sums -- the column pass over a rank's own rows
+// needs only that rank's a, so it does not have to wait for the gather.  Because the state is replicated, the convergence checks and
 // the whole state machine (k_check) run unchanged and identically on every rank: no further collective.
 // =================================================================================================
 __global__ void k_export_slice(const double *__restrict__ src, double *__restrict__ dst, int n, int lo, int hi) {
@@ -376,9 +377,10 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
 enum OnlineOp {
     kOpBeginA = 0,      // rescale coordinates if eps changed; final stage: S0 row partials of the slice -> exch[I]
     kOpBeginB = 1,      // take the reduced S0 partials; mark the kernel as current
-    kOpRow = 2,         // row half-step on the slice; a slice -> exch[I]
-    kOpColPartial = 3,  // take the gathered a; partial column sums over the slice -> exch[J]
-    kOpColFinish = 4,   // take the reduced column sums; b update; close the iteration
+    kOpRow = 2,         // row half-step on the slice; a slice and its row sums -> exch[0 : 2I]
+    kOpColPartial = 3,  // partial column sums over the slice (own rows' a only) -> exch[2I : 2I + J]
+    kOpColFinish = 4,   // after ONE all-reduce of exch[0 : 2I + J]: take the gathered a and the reduced column
+                        // sums; b update; close the iteration
     kOpGapRows = 5,     // final stage: row sums of the slice for the duality gap -> exch[I]
     kOpCheck = 6,       // take the gathered row sums; run the state machine
     kOpFinalRows = 7    // coupling row sums of the slice -> exch[I]
@@ -422,15 +424,15 @@ int online_step(OnlineSolve *S, int op, double *exch) {
             break;
         case kOpColPartial:
             WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            k_import_a<<<bi, 256, 0, st>>>(V, c, exch);
-            WOTB_CUDA(cudaMemsetAsync(exch, 0, (size_t)J * 8, st));
-            P.col_pass(st, V, c, 4, exch);
-            S->launches += 2;
+            WOTB_CUDA(cudaMemsetAsync(exch + 2 * (size_t)I, 0, (size_t)J * 8, st));
+            P.col_pass(st, V, c, 4, exch + 2 * (size_t)I);
+            S->launches += 1;
             break;
         case kOpColFinish:
             WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch);
-            S->launches += 1;
+            k_import_a<<<bi, 256, 0, st>>>(V, c, exch);
+            k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch + 2 * (size_t)I);
+            S->launches += 2;
             break;
         case kOpGapRows:  // kept for ABI stability: the row sums of the gap now ride on kOpRow (lazy check)
             break;

@@ -9,7 +9,7 @@ Two partitionings (BASELINE.json north_star):
 
 2. One very large pair is row-sharded: `sharded_online_solve` drives the stepping entry points of the
    library (wotb_online_*): each rank computes its slice of rows with the online kernel and the ranks
-   exchange two float64 vectors per Sinkhorn iteration with an NCCL all-reduce over NVLink.
+   exchange one float64 vector (2 I + J entries) per Sinkhorn iteration with an NCCL all-reduce over NVLink.
 """
 from __future__ import annotations
 
@@ -287,7 +287,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         prm = _lib.make_params(solver=solver, kernel=_lib.KERNEL_ONLINE, **params)
         f = torch.empty(n_i, dtype=torch.float64, device=dev)
         g = torch.empty(n_j, dtype=torch.float64, device=dev)
-        exch = torch.zeros(max(2 * n_i, n_j), dtype=torch.float64, device=dev)
+        exch = torch.zeros(2 * n_i + n_j, dtype=torch.float64, device=dev)
         solve = C.c_void_p()
         _lib.check(lib.wotb_online_open(h, P(X0), n_i, P(X1), n_j, d, median, P(Gd), C.byref(prm), rank, world, P(f),
                                         P(g), C.byref(solve)))
@@ -310,10 +310,9 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                     reduce(n_i)
                 step(OP_BEGIN_B)
                 for _ in range(slots):
-                    step(OP_ROW)
-                    reduce(2 * n_i)      # a-slices and their row sums (lazy duality-gap check)
-                    step(OP_COL_PARTIAL)
-                    reduce(n_j)
+                    step(OP_ROW)             # a for this rank's rows (+ their row sums, for the lazy gap check)
+                    step(OP_COL_PARTIAL)     # needs only this rank's a: no exchange in between
+                    reduce(2 * n_i + n_j)    # ONE all-reduce per iteration: gathered a | row sums | column sums
                     step(OP_COL_FINISH)
                 step(OP_CHECK)
                 _lib.check(lib.wotb_online_state(solve, C.byref(info), C.byref(done)))
