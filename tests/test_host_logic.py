@@ -121,3 +121,40 @@ def test_synthetic_generators_are_deterministic():
     pairs = synthetic.atlas_pairs()
     assert len(pairs) == 39 and all(5000 <= p[0] <= 20000 and 5000 <= p[1] <= 20000 for p in pairs)
     assert pairs[0][1] == pairs[1][0]            # consecutive days share a population
+
+
+def test_sklearn_solver_policy_matches_installed_sklearn():
+    """ot.util.sklearn_solver_choice decides whether compute_pca may take the GPU path (only where scikit-learn's
+    svd_solver='auto' itself runs the randomized solver).  Checked against what the installed PCA actually picks."""
+    import sklearn.decomposition
+    from wot_b200.ot import util
+    rng = np.random.default_rng(0)
+    for n_samples, n_features, k in [(300, 620, 30), (60, 400, 10), (700, 580, 10), (520, 40, 30), (2000, 90, 30),
+                                     (501, 300, 30), (40, 600, 38)]:
+        pca = sklearn.decomposition.PCA(n_components=min(k, n_samples, n_features), random_state=58951)
+        pca.fit(rng.standard_normal((n_samples, n_features)))
+        assert util.sklearn_solver_choice(n_samples, n_features, min(k, n_samples, n_features)) == pca._fit_svd_solver, \
+            (n_samples, n_features, k, pca._fit_svd_solver)
+
+
+def test_kernel_policy_and_day_slices():
+    from wot_b200.ot import optimal_transport as wot_ot
+    from wot_b200.ot.ot_model import _rows_key
+    assert wot_ot.resolve_kernel("auto", 1000, 1000, 30, 0.05) == "online"
+    assert wot_ot.resolve_kernel("auto", 1000, 1000, 30, 0.01) == "stored"      # exponent error grows like 1/eps
+    assert wot_ot.resolve_kernel("auto", 1000, 1000, 47, 0.05) == "stored"      # beyond the tcgen05 K budget
+    assert wot_ot.resolve_kernel("stored", 1000, 1000, 30, 0.05) == "stored"
+    assert wot_ot._kernel_id("online_simt") == (wot_ot._lib.KERNEL_ONLINE, True)
+    with pytest.raises(ValueError):
+        wot_ot._kernel_id("fast")
+    mask = np.array([False, True, True, True, False])
+    assert _rows_key(mask) == slice(1, 4)                                        # one run of rows: a view
+    scattered = np.array([True, False, True, False, False])
+    assert _rows_key(scattered) is scattered                                     # otherwise the mask itself
+    assert _rows_key(np.zeros(3, dtype=bool)) is not None
+
+
+def test_cli_additive_flags():
+    from wot_b200.commands import optimal_transport as cli
+    args = cli.create_parser().parse_args(["--matrix", "m.txt", "--cell_days", "d.txt", "--streams", "3", "--kernel", "auto"])
+    assert args.streams == 3 and args.kernel == "auto" and args.format == "h5ad" and args.out == "./tmaps"
