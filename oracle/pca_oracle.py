@@ -11,8 +11,10 @@ randomized_range_finder; Halko, Martinsson, Tropp 2011, algorithms 4.3/4.4/5.1):
   n_iter times: Q = normalise(M Q); Q = normalise(M^T Q);  Q = qr(M Q);  B = Q^T M;  svd(B) -> components, singular values.
 sklearn normalises with a pivoted LU between power iterations; any normaliser that keeps the span gives the same
 range (and therefore the same components up to sign and roundoff), so this restatement and the CUDA path use
-Cholesky-QR.  PINNED by tests/test_oracle.py::test_pca_restatement_matches_sklearn against the installed
-scikit-learn executing the reference's own call (cost-matrix level, sign-invariant)."""
+Cholesky-QR.  PINNED twice: tests/test_oracle.py::test_pca_restatement_matches_reference_golden against fixtures produced by
+the unmodified reference's wot.ot.compute_pca (tests/golden/pca_randomized.npz, make_golden.py pca_cases), and
+::test_pca_restatement_matches_sklearn against the installed scikit-learn executing the reference's own call
+(cost-matrix level, sign-invariant)."""
 import numpy as np
 
 

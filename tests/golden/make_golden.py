@@ -244,7 +244,26 @@ def model_cases():
     save("otmodel_3x3", tmap=tm.X, g0=tm.obs["g0"].values, g1=tm.obs["g1"].values)
 
 
+def pca_cases():
+    """Local PCA through the UNMODIFIED reference (wot.ot.compute_pca, wot/ot/util.py:240-255) at shapes where
+    scikit-learn's svd_solver='auto' runs its randomized solver -- the path csrc/pca.cu restates on the GPU.  Both
+    orientations of randomized_svd(transpose='auto'): more cells than genes, and fewer."""
+    wot = import_ref_wot()
+    out = {}
+    for tag, cells, genes, k in (("tall", [600, 700], 300, 30), ("wide", [300, 280], 700, 10)):
+        X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=3)
+        p0, p1, pca, mean = wot.ot.compute_pca(X[day == 0], X[day == 1], k)
+        assert pca._fit_svd_solver == "randomized"
+        out.update({tag + "_cells": np.array(cells), tag + "_genes": np.array(genes), tag + "_k": np.array(k),
+                    tag + "_pca0": p0, tag + "_pca1": p1, tag + "_sv": pca.singular_values_, tag + "_mean": mean})
+    save("pca_randomized", seed=np.array(3), **out)
+
+
 if __name__ == "__main__":
     np.seterr(all="ignore")
-    solver_cases(load_ref_solver_module())
-    model_cases()
+    if len(sys.argv) > 1 and sys.argv[1] == "pca":
+        pca_cases()
+    else:
+        solver_cases(load_ref_solver_module())
+        model_cases()
+        pca_cases()

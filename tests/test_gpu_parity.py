@@ -594,3 +594,19 @@ def test_nan_gap_raises_like_the_reference(ot):
     # the context stays usable after the error
     tmap, _ = _solve(ot, "optimal_transport_duality_gap", C, G)
     assert np.isfinite(tmap).all()
+
+
+@pytest.mark.parametrize("tag", ["tall", "wide"])
+def test_gpu_pca_vs_reference_golden(golden, tag):
+    """csrc/pca.cu against tests/golden/pca_randomized.npz (the unmodified reference's wot.ot.compute_pca,
+    util.py:240-255, randomized-solver shapes in both orientations): same signs, loadings, singular values."""
+    from wot_b200 import synthetic
+    from wot_b200.ot import util
+    g = golden("pca_randomized")
+    cells, genes, k = [int(c) for c in g[tag + "_cells"]], int(g[tag + "_genes"]), int(g[tag + "_k"])
+    X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=int(g["seed"]))
+    q0, q1, pca, mean = util.compute_pca(X[day == 0], X[day == 1], k)
+    assert isinstance(pca, util.LocalPCA)
+    np.testing.assert_allclose(pca.singular_values_, g[tag + "_sv"], rtol=1e-10)
+    np.testing.assert_allclose(mean, g[tag + "_mean"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(np.vstack([q0, q1]), np.vstack([g[tag + "_pca0"], g[tag + "_pca1"]]), rtol=0, atol=1e-8)

@@ -128,3 +128,21 @@ def test_pca_restatement_matches_sklearn(cells, genes, k):
     want = wot_oracle.compute_default_cost_matrix(p1, p2, np.diag(pca.singular_values_))
     got = wot_oracle.compute_default_cost_matrix(q1, q2, np.diag(sv))
     np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["tall", "wide"])
+def test_pca_restatement_matches_reference_golden(golden, tag):
+    """oracle/pca_oracle.py against tests/golden/pca_randomized.npz, produced by the UNMODIFIED reference's
+    wot.ot.compute_pca (make_golden.py pca_cases): loadings up to sign, singular values, gene means."""
+    from oracle import pca_oracle
+    from wot_b200 import synthetic
+    g = golden("pca_randomized")
+    cells, genes, k = [int(c) for c in g[tag + "_cells"]], int(g[tag + "_genes"]), int(g[tag + "_k"])
+    X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=int(g["seed"]))
+    q0, q1, sv, mean = pca_oracle.compute_pca(X[day == 0], X[day == 1], k)
+    np.testing.assert_allclose(sv, g[tag + "_sv"], rtol=1e-11)
+    np.testing.assert_allclose(mean, g[tag + "_mean"], rtol=0, atol=1e-13)
+    want = np.vstack([g[tag + "_pca0"], g[tag + "_pca1"]])
+    got = np.vstack([q0, q1])
+    sign = np.sign((got * want).sum(axis=0))
+    np.testing.assert_allclose(got * sign, want, rtol=0, atol=1e-9)
