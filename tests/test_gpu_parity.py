@@ -610,3 +610,40 @@ def test_gpu_pca_vs_reference_golden(golden, tag):
     np.testing.assert_allclose(pca.singular_values_, g[tag + "_sv"], rtol=1e-10)
     np.testing.assert_allclose(mean, g[tag + "_mean"], rtol=0, atol=1e-13)
     np.testing.assert_allclose(np.vstack([q0, q1]), np.vstack([g[tag + "_pca0"], g[tag + "_pca1"]]), rtol=0, atol=1e-8)
+
+
+def test_cli_optimal_transport_end_to_end(ot, tmp_path):
+    """`wot optimal_transport` (wot/commands/optimal_transport.py:12-30) through `python -m wot_b200 optimal_transport`:
+    matrix + cell_days + growth-rate files in, '{out}_{t0}_{t1}.npz' per day-pair and '{out}_g.txt' out, equal to
+    the model API on the same inputs."""
+    import os
+    import subprocess
+    import sys
+    from wot_b200 import synthetic
+    from wot_b200._anndata import AnnData
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    X, day, growth = synthetic.expression_matrix([260, 300, 280], n_genes=60, seed=31)
+    ids = ["c%d" % i for i in range(len(day))]
+    genes = ["g%d" % i for i in range(X.shape[1])]
+    pd.DataFrame(X, index=ids, columns=genes).to_csv(tmp_path / "matrix.txt", sep="\t", index_label="id")
+    pd.DataFrame({"day": day}, index=ids).to_csv(tmp_path / "days.txt", sep="\t", index_label="id")
+    pd.DataFrame({"cell_growth_rate": growth}, index=ids).to_csv(tmp_path / "growth.txt", sep="\t", index_label="id")
+    cmd = [sys.executable, "-m", "wot_b200", "optimal_transport", "--matrix", str(tmp_path / "matrix.txt"),
+           "--cell_days", str(tmp_path / "days.txt"), "--cell_growth_rates", str(tmp_path / "growth.txt"),
+           "--growth_iters", "2", "--local_pca", "12", "--epsilon", "0.06", "--format", "npz", "--out", str(tmp_path / "tm")]
+    run = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    names = sorted(n for n in os.listdir(tmp_path) if n.startswith("tm_"))
+    assert names == ["tm_0.0_1.0.npz", "tm_1.0_2.0.npz", "tm_g.txt"]
+    # the text round trip keeps float64 to repr precision, so the API on the parsed matrix gives the same maps
+    parsed = pd.read_csv(tmp_path / "matrix.txt", sep="\t", index_col=0)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=ids)
+    model = ot.OTModel(AnnData(parsed.values, obs, pd.DataFrame(index=genes)), growth_iters=2, local_pca=12, epsilon=0.06)
+    for t0, t1 in ((0.0, 1.0), (1.0, 2.0)):
+        want = model.compute_transport_map(t0, t1)
+        got = np.load(tmp_path / ("tm_%s_%s.npz" % (t0, t1)), allow_pickle=True)
+        np.testing.assert_allclose(got["X"], np.asarray(want.X), rtol=1e-9, atol=0)
+        assert list(got["obs_columns"]) == ["g0", "g1", "g2"]
+        np.testing.assert_allclose(got["obs_values"], want.obs.values, rtol=1e-9)
+    g = pd.read_csv(tmp_path / "tm_g.txt", sep="\t", index_col="id")
+    assert list(g.columns) == ["g0", "g1", "g2"] and len(g) == 260 + 300
