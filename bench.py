@@ -287,6 +287,9 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from wot_b200.pipeline import Pipeline
     # measured on B200 (profiles/r1h): two online solves in flight 7.28 tmaps/s vs 6.50 serial, three 6.66; the
