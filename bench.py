@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """Benchmark of the transport-map hot path (BASELINE.json metric: day-pair tmaps/s and Sinkhorn
-iterations/s at 1/2/4/8 B200, fraction of the HBM roofline).
+iterations/s at 1/2/4/8 B200, fraction of the HBM or MUFU roofline).
 
 Workload (config.workload): BASELINE.json configs[1], the reprogramming-atlas-shaped
 compute_all_transport_maps: 39 day-pairs, 5-20k cells per day (seed 1), 30 local-PCA coordinates,
 defaults eps=0.05 lambda1=1 lambda2=50, growth_iters=3.  A STEP is one day-pair transport map:
 median-normalised cost + 3 cold-start duality-gap solves + coupling and growth row sums.  Steps walk the
 39 pairs in order; with N GPUs rank r takes pair (step*N + r) mod 39 ("independent day-pairs shard one
-per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.
+per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.  Every GPU keeps `--streams` (2)
+day-pairs in flight on separate CUDA streams (wot_b200.pipeline; a step is still one day-pair).
 
-  value  tmaps/s with the pair's coordinates already in HBM, timed with CUDA events on the library's
-         stream, max over ranks.
+  value  tmaps/s with every pair's coordinates already in HBM, timed with CUDA events on the library's
+         streams (earliest start to latest end), max over ranks.
   e2e    the same through the host-buffer C-ABI call (wotb_transport_map_from_coords_host): coordinates
-         copied from pinned host memory, the float64 coupling, growth rows and potentials copied back.
+         copied from pinned host memory, the float64 coupling, growth rows and potentials copied back; one more
+         context than `--streams` so that a coupling crosses PCIe while the solves keep the SMs (compute slots).
   roofline  the dominant kernel of the selected variant, measured live on the mean atlas shape:
             --kernel online (default): k_online_tc, one half-iteration pass that recomputes exp2 of all I*J
             entries from coordinates on tcgen05 + MUFU; bound = MUFU.EX2 throughput (BASELINE.json names the

@@ -145,7 +145,8 @@ def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tole
 
 
 class Context:
-    """One wotb_ctx (one per process and device)."""
+    """One wotb_ctx: a CUDA stream plus grow-only workspaces.  The process-wide default (context()) serves plain calls;
+    wot_b200.pipeline creates one per worker thread.  A context is not thread-safe."""
 
     def __init__(self, device=0, stream=None):
         lib = load()
