@@ -647,3 +647,19 @@ def test_cli_optimal_transport_end_to_end(ot, tmp_path):
         np.testing.assert_allclose(got["obs_values"], want.obs.values, rtol=1e-9)
     g = pd.read_csv(tmp_path / "tm_g.txt", sep="\t", index_col="id")
     assert list(g.columns) == ["g0", "g1", "g2"] and len(g) == 260 + 300
+
+
+def test_gpu_pca_rank_deficient_input_is_handed_to_sklearn(caplog):
+    """An expression matrix of rank 20 cannot feed 40 independent test vectors: the Cholesky-QR of the range finder
+    reports it, backend='gpu' raises, backend='auto' logs a warning and returns scikit-learn's result."""
+    import logging
+    from wot_b200.ot import util
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((1300, 20)) @ rng.standard_normal((20, 300))
+    m1, m2 = X[:600], X[600:]
+    with pytest.raises(ValueError, match="not positive definite"):
+        util.compute_pca(m1, m2, 30, backend="gpu")
+    with caplog.at_level(logging.WARNING, logger="wot"):
+        p1, p2, pca, _ = util.compute_pca(m1, m2, 30)
+    assert "rank-deficient" in caplog.text and not isinstance(pca, util.LocalPCA)
+    assert p1.shape == (600, 30) and p2.shape == (700, 30)

@@ -10,6 +10,7 @@ solver, stay on scikit-learn.
 from __future__ import annotations
 
 import ctypes as C
+import logging
 
 import numpy as np
 import scipy.sparse
@@ -100,9 +101,19 @@ def compute_pca(m1, m2, n_components, backend="auto"):
     n1, n2 = m1.shape[0], m2.shape[0]
     genes = m1.shape[1]
     k = min(int(n_components), n1 + n2)
-    if backend == "auto":
+    auto = backend == "auto"
+    if auto:
         fits = k + N_OVERSAMPLES <= min(64, genes, n1 + n2)
         backend = "gpu" if fits and sklearn_solver_choice(genes, n1 + n2, k) == "randomized" else "sklearn"
     if backend == "sklearn":
         return compute_pca_sklearn(m1, m2, n_components)
-    return compute_pca_gpu(m1, m2, n_components)
+    try:
+        return compute_pca_gpu(m1, m2, n_components)
+    except ValueError as exc:
+        # numerically rank-deficient input (fewer independent cells or genes than k + 10 test vectors): the
+        # Cholesky-QR of the range finder has no positive pivot.  scikit-learn's LU/QR complete such a basis
+        # arbitrarily; that case is left to it rather than imitated.
+        if auto and "not positive definite" in str(exc):
+            logging.getLogger("wot").warning("local PCA: rank-deficient input, using scikit-learn (%s)", exc)
+            return compute_pca_sklearn(m1, m2, n_components)
+        raise
