@@ -31,6 +31,7 @@ constexpr int kPcaMaxS = 64;   // k + n_oversamples <= 64
 constexpr int kPcaKc = 32;     // reduction chunk staged in shared memory
 constexpr int kPcaRows = 64;   // output rows (cells or genes) per CTA
 constexpr int kPcaSlab = 512;  // cells per CTA of the A^T Y product
+constexpr int kPcaGramRows = 128;  // rows per CTA of the Gram product (enough CTAs to fill the GPU for the tall side)
 
 // ---- centring -----------------------------------------------------------------------------------------------------
 // column sums of X[n, g] over a slab of rows -> part[slab][g]
@@ -205,11 +206,13 @@ __global__ void __launch_bounds__(256) k_pca_gram(const double *__restrict__ T, 
 }
 
 // ---- one CTA: Gram (s x s, leading dimension sp) = R^T R;  W = R^-1 (upper triangular), padded with zeros ----------
-__global__ void __launch_bounds__(64) k_pca_chol_inv(const double *__restrict__ Gram, int s, int sp, double *__restrict__ W,
-                                                     int *__restrict__ fail) {
+// 1024 threads as a 32 x 32 grid, thread (ty, tx) owns the 2 x 2 block of rows {ty, ty + 32} x columns {tx, tx + 32}
+// in the rank-1 updates; the triangular inverse runs one warp per column, dot products by warp shuffle.
+__global__ void __launch_bounds__(1024) k_pca_chol_inv(const double *__restrict__ Gram, int s, int sp, double *__restrict__ W,
+                                                       int *__restrict__ fail) {
     __shared__ double L[kPcaMaxS][kPcaMaxS + 1];  // lower Cholesky factor, Gram = L L^T, R = L^T
-    const int t = threadIdx.x;
-    for (int e = t; e < kPcaMaxS * kPcaMaxS; e += blockDim.x) {
+    const int t = threadIdx.x, tx = t & 31, ty = t >> 5;
+    for (int e = t; e < kPcaMaxS * kPcaMaxS; e += 1024) {
         const int r = e / kPcaMaxS, c = e % kPcaMaxS;
         L[r][c] = (r < s && c < s) ? Gram[r * sp + c] : 0.0;
     }
@@ -221,45 +224,57 @@ __global__ void __launch_bounds__(64) k_pca_chol_inv(const double *__restrict__ 
             L[j][j] = sqrt(d > 0.0 ? d : 1.0);
         }
         __syncthreads();
-        const double djj = L[j][j];
-        if (t > j && t < s) L[t][j] /= djj;
+        if (t > j && t < s) L[t][j] /= L[j][j];
         __syncthreads();
-        if (t > j && t < s) {
-            const double ltj = L[t][j];
-            for (int c = j + 1; c <= t; ++c) L[t][c] -= ltj * L[c][j];
-        }
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr)
+#pragma unroll
+            for (int dc = 0; dc < 2; ++dc) {
+                const int r = ty + 32 * dr, c = tx + 32 * dc;
+                if (r > j && r < s && c > j && c <= r) L[r][c] -= L[r][j] * L[c][j];
+            }
         __syncthreads();
     }
-    // W = R^-1 = (L^T)^-1 = (L^-1)^T: thread t solves L x = e_t (forward substitution); x is column t of L^-1,
-    // i.e. row t of W (upper triangular), padded with zeros
-    for (int e = t; e < sp * sp; e += blockDim.x) W[e] = 0.0;
+    // W = R^-1 = (L^-1)^T.  Warp w solves L x = e_col for col = w, w + 32 by forward substitution: x_i needs the dot
+    // product of row i of L with the x found so far, lanes hold x_lane and x_{lane + 32}.
+    for (int e = t; e < sp * sp; e += 1024) W[e] = 0.0;
     __syncthreads();
-    if (t < s) {
-        double x[kPcaMaxS];
-        for (int i = t; i < s; ++i) {
-            double v = i == t ? 1.0 : 0.0;
-            for (int c = t; c < i; ++c) v -= L[i][c] * x[c];
-            x[i] = v / L[i][i];
-            W[t * sp + i] = x[i];
+    for (int col = ty; col < s; col += 32) {
+        double x0 = 0.0, x1 = 0.0;  // x[tx], x[tx + 32]
+        for (int i = col; i < s; ++i) {
+            double part = 0.0;
+            if (tx >= col && tx < i) part += L[i][tx] * x0;
+            if (tx + 32 >= col && tx + 32 < i) part += L[i][tx + 32] * x1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const double xi = ((i == col ? 1.0 : 0.0) - part) / L[i][i];
+            if (tx == (i & 31)) {
+                if (i < 32) x0 = xi; else x1 = xi;
+            }
+            if (tx == 0) W[col * sp + i] = xi;
         }
     }
 }
 
-// ---- T[rows, sp] <- T W  (W [sp, sp_out], row-major with leading dimension ldw);  one thread per row ---------------
-__global__ void __launch_bounds__(128) k_pca_apply(const double *__restrict__ T, long long rows, int sp, const double *__restrict__ W,
+// ---- Out[rows, n_out] = T[rows, sp] W  (W [sp, ldw] row-major; Out may alias T when ld_out == sp) -----------------
+// CTA: 16 rows staged in shared memory; thread (r, g) of 16 x 16 computes outputs g, g + 16, ... of row r.
+__global__ void __launch_bounds__(256) k_pca_apply(const double *__restrict__ T, long long rows, int sp, const double *__restrict__ W,
                                                    int ldw, int n_out, int ld_out, double *__restrict__ Out) {
     __shared__ double Ws[kPcaMaxS * kPcaMaxS];
-    for (int e = threadIdx.x; e < sp * ldw; e += blockDim.x) Ws[e] = W[e];
-    __syncthreads();
-    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= rows) return;
-    double t[kPcaMaxS];
-#pragma unroll 8
-    for (int c = 0; c < sp; ++c) t[c] = T[row * sp + c];
-    for (int o = 0; o < n_out; ++o) {
+    __shared__ double Ts[16][kPcaMaxS + 1];
+    const long long row0 = (long long)blockIdx.x * 16;
+    for (int e = threadIdx.x; e < sp * ldw; e += 256) Ws[e] = W[e];
+    for (int e = threadIdx.x; e < 16 * sp; e += 256) {
+        const int r = e / sp, c = e % sp;
+        Ts[r][c] = row0 + r < rows ? T[(row0 + r) * sp + c] : 0.0;
+    }
+    __syncthreads();  // every input of this CTA's rows is in shared memory: writing Out over T is safe from here on
+    const int r = threadIdx.x >> 4, g = threadIdx.x & 15;
+    if (row0 + r >= rows) return;
+    for (int o = g; o < n_out; o += 16) {
         double v = 0.0;
-        for (int c = 0; c < sp; ++c) v = fma(t[c], Ws[c * ldw + o], v);
-        Out[row * ld_out + o] = v;
+        for (int c = 0; c < sp; ++c) v = fma(Ts[r][c], Ws[c * ldw + o], v);
+        Out[(row0 + r) * ld_out + o] = v;
     }
 }
 
@@ -313,7 +328,7 @@ struct PcaWork {
 };
 
 static void pca_gram(const PcaWork &w, const double *T, long long rows) {
-    const int rps = 2048;
+    const int rps = kPcaGramRows;
     const int slabs = (int)cdiv(rows, rps);
     k_pca_gram<<<slabs, dim3(w.sp / 4, w.sp / 4), 0, w.st>>>(T, rows, w.sp, rps, w.part);
     k_pca_reduce<<<(unsigned)cdiv((long long)w.sp * w.sp, 256), 256, 0, w.st>>>(w.part, slabs, (long long)w.sp * w.sp, 1.0, w.gram);
@@ -323,8 +338,8 @@ static void pca_gram(const PcaWork &w, const double *T, long long rows) {
 static void pca_orth(const PcaWork &w, double *T, long long rows) {
     for (int round = 0; round < 2; ++round) {
         pca_gram(w, T, rows);
-        k_pca_chol_inv<<<1, 64, 0, w.st>>>(w.gram, w.s, w.sp, w.W, w.fail);
-        k_pca_apply<<<(unsigned)cdiv(rows, 128), 128, 0, w.st>>>(T, rows, w.sp, w.W, w.sp, w.sp, w.sp, T);
+        k_pca_chol_inv<<<1, 1024, 0, w.st>>>(w.gram, w.s, w.sp, w.W, w.fail);
+        k_pca_apply<<<(unsigned)cdiv(rows, 16), 256, 0, w.st>>>(T, rows, w.sp, w.W, w.sp, w.sp, w.sp, T);
     }
 }
 
@@ -352,7 +367,7 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
     const bool transpose = G < N;  // randomized_svd(transpose='auto'): work on the matrix with more rows than columns
     const int sp = (int)round_up(size, 4);
     const long long small = transpose ? G : N, tall = transpose ? N : G;
-    const int slabs_aty = (int)cdiv(N, kPcaSlab), slabs_gram = (int)cdiv(tall, 2048), slabs_col = (int)cdiv(N, 256);
+    const int slabs_aty = (int)cdiv(N, kPcaSlab), slabs_gram = (int)cdiv(tall, kPcaGramRows), slabs_col = (int)cdiv(N, 256);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         const size_t at = off;
@@ -362,7 +377,7 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
     const size_t o_A = take((size_t)N * G * 8), o_mu = take((size_t)G * 8);
     const size_t o_Y = take((size_t)N * sp * 8), o_Z = take((size_t)G * sp * 8);
     size_t part_bytes = (size_t)slabs_aty * G * sp * 8;
-    part_bytes = std::max(part_bytes, (size_t)std::max(slabs_gram, (int)cdiv(std::max(N, (long long)G), 2048)) * sp * sp * 8);
+    part_bytes = std::max(part_bytes, (size_t)std::max(slabs_gram, (int)cdiv(std::max(N, (long long)G), kPcaGramRows)) * sp * sp * 8);
     part_bytes = std::max(part_bytes, (size_t)slabs_col * G * 8);
     const size_t o_part = take(part_bytes), o_gram = take((size_t)sp * sp * 8), o_W = take((size_t)kPcaMaxS * kPcaMaxS * 8);
     const size_t o_fail = take(256);
@@ -424,7 +439,7 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
     WOTB_CUDA(cudaMemcpyAsync(w.W, Wh.data(), Wh.size() * 8, cudaMemcpyHostToDevice, st));
     const double *src = transpose ? Qt : Qs;  // [N, sp] either way
     double *comp_dev = w.part;                // [N, k]
-    k_pca_apply<<<(unsigned)cdiv(N, 128), 128, 0, st>>>(src, N, sp, w.W, k, k, k, comp_dev);
+    k_pca_apply<<<(unsigned)cdiv(N, 16), 256, 0, st>>>(src, N, sp, w.W, k, k, k, comp_dev);
     WOTB_CUDA(cudaMemcpyAsync(comp_host, comp_dev, (size_t)N * k * 8, cudaMemcpyDeviceToHost, st));
     if (gene_means_host) WOTB_CUDA(cudaMemcpyAsync(gene_means_host, w.mu, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
     WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
