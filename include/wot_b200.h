@@ -124,11 +124,12 @@ void wotb_set_pdl(int32_t on);
  * below, size] is the Gaussian test matrix numpy.random.RandomState(58951).normal(size=(short side, size))
  * made by the caller so that the result equals scikit-learn's up to sign and roundoff; "short side" is genes
  * when genes < n1 + n2, else n1 + n2.  Outputs: comp [n1 + n2, k] = pca.components_.T (util.py:250),
- * singular_values [k] (ot_model.py:301), gene_means [genes] (util.py:245; may be NULL), gpu_ms (may be NULL).
+ * singular_values [k] (ot_model.py:301), gene_means [genes] (util.py:245; may be NULL), cell_means [n1 + n2] =
+ * sklearn's pca.mean_, the per-cell mean over genes of the gene-centred matrix (may be NULL), gpu_ms (may be NULL).
  * Everything is float64 and reduced in a fixed order (deterministic). */
 int wotb_pca_host(wotb_ctx *ctx, const double *m1_host, int64_t n1, const double *m2_host, int64_t n2, int64_t genes,
                   int32_t k, const double *q0_host, int32_t size, int32_t n_iter, double *comp_host,
-                  double *singular_values_host, double *gene_means_host, double *gpu_ms);
+                  double *singular_values_host, double *gene_means_host, double *cell_means_host, double *gpu_ms);
 
 /* ---- cost: replaces OTModel.compute_default_cost_matrix, ot_model.py:242-253 ------------------
  * x0 [I,d], x1 [J,d] float64 row-major; scale [d] = singular values (the diagonal of `eigenvals`,
@@ -244,7 +245,8 @@ int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, dou
 
 /* Kernel-level hook for tests and bench.py: one online-kernel pass (the K.(b dy) half of optimal_transport.py:133
  * without materialising K),  sums[i] = sum_j exp2(off_out[i] + off_in[j] + scale^2 <x_out_i, x_in_j>),  all device
- * pointers, float64.  impl 0: SIMT FP32 kernel, impl 1: tcgen05 (3xTF32 cross term + offsets in TMEM; d <= 38).
+ * pointers, float64.  impl 0: SIMT FP32 kernel, impl 1 / 2: tcgen05 kernel with 8 / 16 epilogue warps (fp16 split operands,
+ * cross term + offsets accumulated in TMEM; d <= 46).
  * ms_per_pass (may be NULL) = average device time of `reps` launches after one warm-up (CUDA events on the
  * context's stream). */
 int wotb_online_rowsums_dev(wotb_ctx *ctx, const double *x_out, int64_t n_out, const double *x_in, int64_t n_in, int32_t d,

@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--time", nargs="*", default=["12486x12405"])
     ap.add_argument("--d", type=int, default=30)
     ap.add_argument("--impls", default="0,1")
+    ap.add_argument("--eps", type=float, nargs="*", default=[0.05], help="epsilon of the --check states")
     args = ap.parse_args()
     import torch
     ctx = _lib.context(0)
@@ -68,13 +69,17 @@ def main():
     print("MUFU.EX2 peak (measured): %.3f T ex2/s" % (peak.value / 1e12), flush=True)
     for shape in args.check:
         n_out, n_in = (int(v) for v in shape.split("x"))
-        x0, x1, scale, po, pi = make_inputs(n_out, n_in, args.d, seed=5)
-        want = reference(x0, x1, scale, po, pi)
-        for impl in impls:
-            got, ms = run(ctx, torch, x0, x1, scale, po, pi, impl, 1)
-            err = np.abs(got - want) / want
-            print("check %6d x %6d d=%d %-14s max rel err %.3e  mean %.3e  (sum range %.3g..%.3g)"
-                  % (n_out, n_in, args.d, names[impl], err.max(), err.mean(), want.min(), want.max()), flush=True)
+        for eps in args.eps:
+            x0, x1, scale, po, pi = make_inputs(n_out, n_in, args.d, seed=5, eps=eps)
+            want = reference(x0, x1, scale, po, pi)
+            for impl in impls:
+                got, ms = run(ctx, torch, x0, x1, scale, po, pi, impl, 1)
+                ok = want > 1e-30
+                err = np.abs(got[ok] - want[ok]) / want[ok]
+                bias = float(np.mean((got[ok] - want[ok]) / want[ok]))
+                print("check %6d x %6d d=%d eps=%g %-14s max rel err %.3e  mean %.3e  bias %+.3e  (sum range %.3g..%.3g)"
+                      % (n_out, n_in, args.d, eps, names[impl], err.max(), err.mean(), bias, want[ok].min(), want.max()),
+                      flush=True)
     for shape in args.time:
         n_out, n_in = (int(v) for v in shape.split("x"))
         x0, x1, scale, po, pi = make_inputs(n_out, n_in, args.d, seed=6)

@@ -24,6 +24,11 @@ except Exception:  # anndata (and h5py) are not installed in the build image
         def shape(self):
             return self.X.shape
 
+        @property
+        def T(self):
+            """Transposed view: cells <-> genes (initialize_ot_model(transpose=True), wot/ot/initializer.py)."""
+            return AnnData(self.X.T, self.var, self.obs)
+
         def copy(self):
             return AnnData(self.X.copy(), self.obs.copy(), self.var.copy())
 
@@ -47,4 +52,10 @@ except Exception:  # anndata (and h5py) are not installed in the build image
             return AnnData(X, obs, var)
 
         def write(self, path):
-            raise ImportError("writing .h5ad needs the anndata package; use output_file_format='npz' or 'txt'")
+            """.h5ad in the layout anndata writes and TransportMapModel.from_directory reads
+            (wot/tmap/transport_map_model.py:709-721), through the built-in HDF5 writer (wot_b200/h5ad.py)."""
+            from . import h5ad
+            h5ad.write_anndata(path, self)
+
+        def write_loom(self, path):
+            raise ImportError("writing .loom needs the anndata and loompy packages; use 'h5ad', 'txt' or 'npz'")

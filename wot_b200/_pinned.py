@@ -1,8 +1,11 @@
 """Pool of page-locked host blocks for coupling outputs.
 
 cudaHostAlloc costs ~0.3 ms per MiB (350 ms for the 1.2 GB coupling of a mean atlas pair, more than solving the
-pair) and synchronises the device, so blocks are recycled: when the last ndarray viewing a block is
-garbage-collected the block returns to the pool (compute_all_transport_maps drops each map after writing it).
+pair) and synchronises the device, so blocks are recycled.  Every array handed out views a fresh `_Lease`
+object; NumPy keeps the object an array was made from as the `.base` of that array and of EVERY view derived
+from it (np.asarray(tmap), tmap.view(np.ndarray), slices, pd.DataFrame(tmap) ...), so the lease lives exactly
+as long as somebody can still read the memory, and its finalizer returns the block to the pool
+(compute_all_transport_maps drops each map after writing it).
 Day-pairs differ in size by up to 16x, so a new block is never smaller than the largest one handed out so far:
 after the first few maps every idle block fits every request and the pool stops allocating.
 """
@@ -15,16 +18,23 @@ import numpy as np
 
 from . import _lib
 
-_free = []          # PinnedArray blocks nobody views
+_free = []          # blocks nobody views
 _lock = threading.Lock()
 _MAX_IDLE = 4
 _largest = 0        # bytes of the largest block allocated so far
 _GRANULE = 64 << 20
+_alloc = None       # block factory: nbytes -> object with .buf (ctypes char array) and .nbytes; tests replace it
 
 
-class _PinnedNd(np.ndarray):
-    """ndarray view that keeps its pinned block alive."""
-    _block = None
+class _Lease:
+    """One loan of a pinned block.  Exposes the block's memory through the buffer protocol (PEP 688) and is
+    the ultimate `.base` of every ndarray viewing it."""
+
+    def __init__(self, block):
+        self._block = block
+
+    def __buffer__(self, flags):
+        return memoryview(self._block.buf)
 
 
 def _give_back(block):
@@ -48,11 +58,11 @@ def empty(shape, dtype):
                 want = max(-(-want // _GRANULE) * _GRANULE, _largest)
                 _largest = want
     if block is None:
-        block = _lib.PinnedArray(want)
-    arr = block.view(shape, dtype).view(_PinnedNd)
-    arr._block = block
-    weakref.finalize(arr, _give_back, block)
-    return arr
+        block = (_alloc or _lib.PinnedArray)(want)
+    lease = _Lease(block)
+    weakref.finalize(lease, _give_back, block)
+    count = int(np.prod(shape))
+    return np.frombuffer(lease, dtype=dtype, count=count).reshape(shape)
 
 
 def drain():

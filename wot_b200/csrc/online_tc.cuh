@@ -21,17 +21,19 @@
 // ~1e-5 absolute at eps = 0.05, the same as the fp32 SIMT kernel; tests/test_gpu_parity.py holds both to
 // the 1e-4 coupling criterion.
 //
-// CTA = 256 out rows (two 128-row A blocks resident in shared memory) x one segment of the in side, which
-// streams through a ring of 128-row B tiles: one cp.async.bulk per tile, because the operand arrays are
-// kept in HBM in exactly the canonical K-major no-swizzle UMMA layout (8-row groups of 16-byte chunks), so
-// a tile is a contiguous 24 KB block.  Per B tile the MMA thread issues 2 x 3*kseg/16 tcgen05.mma
-// (kind::f16, M = 128, N = 128, K = 16) into two of four 128-column TMEM accumulators; eight epilogue
-// warps (one warpgroup per row block, thread = row) drain them with tcgen05.ld, exp2 and an in-thread sum:
-// no shuffles, no shared memory.  L2 traffic is 0.75 byte per entry; nothing of size I x J exists anywhere.
+// CTA (640 threads) = 256 out rows (two 128-row A blocks, double buffered in shared memory) x a contiguous range of
+// (out block, in tile) work units dealt "stream-K" style over a one-wave grid.  The in side streams through a ring
+// of 128-row B tiles: one cp.async.bulk per tile, because the operand arrays are kept in HBM in exactly the
+// canonical K-major no-swizzle UMMA layout (8-row groups of 16-byte chunks), so a tile is a contiguous 24 KB block.
+// Per B tile each of the two MMA warps issues 3*kseg/16 tcgen05.mma (kind::f16, M = 128, N = 128, K = 16) into its
+// row block's half of a double-buffered 2 x 256-column TMEM accumulator (all 512 columns); 16 epilogue warps
+// (8 per row block: thread = row x 64 columns, EW = 8; or 8 warps, thread = row x 128 columns, EW = 4) drain
+// them with tcgen05.ld 32x32b.x32, exp2 and an in-thread sum: no shuffles, no shared memory in the tile loop.
+// L2 traffic is 0.75 byte per entry; nothing of size I x J exists anywhere.
 //
-// Warp roles (384 threads): warp 0 lane 0 TMA producer, warp 1 TMEM allocation + MMA issue (lane 0),
-// warps 4..11 epilogue.  Pipelines: full/empty per B stage (TMA <-> MMA), acc_full/acc_empty per TMEM
-// buffer (MMA <-> epilogue).
+// Warp roles: warp 0 lane 0 TMA producer, warp 1 TMEM allocation, warps 1..2 MMA issue (one per row block, one
+// elected lane), warp 3 idle, warps 4.. epilogue.  Pipelines: full/empty per B stage (TMA <-> MMA), a_full/a_empty
+// per A buffer, acc_full/acc_empty per (TMEM buffer, row block) (MMA <-> epilogue).
 #pragma once
 
 #include <cuda_fp16.h>

@@ -55,7 +55,8 @@ __global__ void k_pca_reduce(const double *__restrict__ part, int n_slabs, long 
 }
 
 // one warp per cell: m = mean over genes of (X - mu);  X <- X - mu - m      (util.py:245-246 + PCA.fit's centring)
-__global__ void k_pca_center(double *__restrict__ X, long long N, int G, const double *__restrict__ mu) {
+__global__ void k_pca_center(double *__restrict__ X, long long N, int G, const double *__restrict__ mu,
+                             double *__restrict__ cell_means) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= N) return;
@@ -65,6 +66,7 @@ __global__ void k_pca_center(double *__restrict__ X, long long N, int G, const d
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const double m = s / (double)G;
+    if (lane == 0) cell_means[row] = m;  // sklearn's PCA.mean_ (one entry per feature of x.T, i.e. per cell)
     for (int g = lane; g < G; g += 32) x[g] = x[g] - mu[g] - m;
 }
 
@@ -355,7 +357,7 @@ static void pca_aty(const PcaWork &w, const double *Yin, double *Zout) {  // [G,
 
 int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int64_t n2, int64_t genes, int k,
              const double *q0, int size, int n_iter, double *comp_host, double *sv_host, double *gene_means_host,
-             double *gpu_ms) {
+             double *cell_means_host, double *gpu_ms) {
     WOTB_REQUIRE(ctx && m1 && m2 && q0 && comp_host && sv_host, "NULL argument");
     const long long N = n1 + n2;
     const int G = (int)genes;
@@ -374,7 +376,7 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
         off += (bytes + 255) / 256 * 256;
         return at;
     };
-    const size_t o_A = take((size_t)N * G * 8), o_mu = take((size_t)G * 8);
+    const size_t o_A = take((size_t)N * G * 8), o_mu = take((size_t)G * 8), o_cm = take((size_t)N * 8);
     const size_t o_Y = take((size_t)N * sp * 8), o_Z = take((size_t)G * sp * 8);
     size_t part_bytes = (size_t)slabs_aty * G * sp * 8;
     part_bytes = std::max(part_bytes, (size_t)std::max(slabs_gram, (int)cdiv(std::max(N, (long long)G), kPcaGramRows)) * sp * sp * 8);
@@ -396,7 +398,8 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
     // centring: gene means over cells (util.py:245), then every cell's mean over genes (PCA.fit on x.T)
     k_pca_colsum<<<dim3((unsigned)cdiv(G, 128), slabs_col), 128, 0, st>>>(w.A, N, G, 256, w.part);
     k_pca_reduce<<<(unsigned)cdiv(G, 256), 256, 0, st>>>(w.part, slabs_col, G, 1.0 / (double)N, w.mu);
-    k_pca_center<<<(unsigned)cdiv(N, 8), 256, 0, st>>>(w.A, N, G, w.mu);
+    double *cell_means = (double *)(base + o_cm);
+    k_pca_center<<<(unsigned)cdiv(N, 8), 256, 0, st>>>(w.A, N, G, w.mu, cell_means);
     // Q0 [small, size] -> padded [small, sp] in the buffer of the short side
     double *Qs = transpose ? w.Z : w.Y, *Qt = transpose ? w.Y : w.Z;  // short-side / tall-side iterates
     WOTB_CUDA(cudaMemsetAsync(Qs, 0, (size_t)small * sp * 8, st));
@@ -442,6 +445,7 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
     k_pca_apply<<<(unsigned)cdiv(N, 16), 256, 0, st>>>(src, N, sp, w.W, k, k, k, comp_dev);
     WOTB_CUDA(cudaMemcpyAsync(comp_host, comp_dev, (size_t)N * k * 8, cudaMemcpyDeviceToHost, st));
     if (gene_means_host) WOTB_CUDA(cudaMemcpyAsync(gene_means_host, w.mu, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
+    if (cell_means_host) WOTB_CUDA(cudaMemcpyAsync(cell_means_host, cell_means, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
     WOTB_CUDA(cudaStreamSynchronize(st));
     WOTB_CUDA(cudaGetLastError());
@@ -457,7 +461,8 @@ int pca_host(wotb_ctx *ctx, const double *m1, int64_t n1, const double *m2, int6
 
 extern "C" int wotb_pca_host(wotb_ctx *ctx, const double *m1_host, int64_t n1, const double *m2_host, int64_t n2, int64_t genes,
                              int32_t k, const double *q0_host, int32_t size, int32_t n_iter, double *comp_host,
-                             double *singular_values_host, double *gene_means_host, double *gpu_ms) {
+                             double *singular_values_host, double *gene_means_host, double *cell_means_host,
+                             double *gpu_ms) {
     return wotb::pca_host(ctx, m1_host, n1, m2_host, n2, genes, k, q0_host, size, n_iter, comp_host, singular_values_host,
-                          gene_means_host, gpu_ms);
+                          gene_means_host, cell_means_host, gpu_ms);
 }

@@ -33,10 +33,19 @@ class LocalPCA:
         self.gpu_ms = gpu_ms
 
 
+def _sklearn_has_covariance_eigh():
+    try:
+        import sklearn
+        major, minor = (int(v) for v in sklearn.__version__.split(".")[:2])
+        return (major, minor) >= (1, 5)
+    except Exception:
+        return True
+
+
 def sklearn_solver_choice(n_samples, n_features, k):
-    """Which solver sklearn 1.x PCA(svd_solver='auto').fit picks for an (n_samples, n_features) matrix
-    (sklearn/decomposition/_pca.py::_fit)."""
-    if n_features <= 1000 and n_samples >= 10 * n_features:
+    """Which solver the INSTALLED scikit-learn's PCA(svd_solver='auto').fit picks for an (n_samples, n_features)
+    matrix (sklearn/decomposition/_pca.py::_fit; the covariance_eigh rule exists from 1.5 on)."""
+    if _sklearn_has_covariance_eigh() and n_features <= 1000 and n_samples >= 10 * n_features:
         return "covariance_eigh"
     if max(n_samples, n_features) <= 500:
         return "full"
@@ -80,14 +89,16 @@ def compute_pca_gpu(m1, m2, n_components, ctx=None):
     comp = np.empty((cells, k))
     sv = np.empty(k)
     gene_means = np.empty(genes)
+    cell_means = np.empty(cells)
     ms = C.c_double()
     ctx = ctx or _lib.context()
     _lib.check(ctx.lib.wotb_pca_host(ctx.handle, _lib.ptr(a), n1, _lib.ptr(b), n2, genes, k, _lib.ptr(q0), size, n_iter,
-                                     _lib.ptr(comp), _lib.ptr(sv), _lib.ptr(gene_means), C.byref(ms)))
+                                     _lib.ptr(comp), _lib.ptr(sv), _lib.ptr(gene_means), _lib.ptr(cell_means),
+                                     C.byref(ms)))
     # svd_flip(u_based_decision=False): the largest-magnitude loading of every component is positive
     top = np.argmax(np.abs(comp), axis=0)
     comp *= np.sign(comp[top, np.arange(k)])
-    pca = LocalPCA(comp.T, sv, genes, None, ms.value)
+    pca = LocalPCA(comp.T, sv, genes, cell_means, ms.value)
     return comp[:n1], comp[n1:], pca, gene_means
 
 

@@ -72,7 +72,13 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
         cost_matrices = [None] * len(day_pairs)
     files = [_io.check_file_extension(os.path.join(tmap_dir, tmap_prefix + "_{}_{}".format(*p)), output_file_format)
              for p in day_pairs]
-    todo = [k for k in range(len(day_pairs)) if overwrite or not os.path.exists(files[k])]  # skip before dispatch
+    # skip before dispatch; rank 0 decides and broadcasts, so that a rank arriving late cannot see files written by
+    # faster ranks in THIS run and deal itself a different assignment
+    todo = [k for k in range(len(day_pairs)) if overwrite or not os.path.exists(files[k])]
+    if world > 1:
+        box = [todo if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        todo = box[0]
     days = model.matrix.obs[model.day_field]
     counts = days.value_counts()
     costs = [float(counts.get(day_pairs[k][0], 0)) * float(counts.get(day_pairs[k][1], 0)) for k in todo]

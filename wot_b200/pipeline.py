@@ -25,6 +25,39 @@ from . import _lib
 _idle_contexts = {}      # device -> [Context]
 _idle_lock = threading.Lock()
 
+# wotb_set_compute_slots / wotb_set_pdl are process-wide library settings; several pipelines may be open at once
+# (two OTModel.compute_all_transport_maps calls in different threads, a parameter sweep alongside), so they are
+# reference counted: slots follow the most recent pipeline that asked for them and return to "no limit" when the
+# last such pipeline closes; programmatic dependent launch stays off while ANY multi-stream pipeline is open.
+_settings_lock = threading.Lock()
+_open_slot_limits = []   # compute_slots of the open pipelines that set one, in opening order
+_open_multi = 0          # open pipelines with more than one stream
+
+
+def _settings_open(slots, multi):
+    global _open_multi
+    lib = _lib.load()
+    with _settings_lock:
+        if slots:
+            _open_slot_limits.append(slots)
+            lib.wotb_set_compute_slots(int(slots))
+        if multi:
+            _open_multi += 1
+            lib.wotb_set_pdl(0)
+
+
+def _settings_close(slots, multi):
+    global _open_multi
+    lib = _lib.load()
+    with _settings_lock:
+        if slots:
+            _open_slot_limits.remove(slots)
+            lib.wotb_set_compute_slots(int(_open_slot_limits[-1]) if _open_slot_limits else 0)
+        if multi:
+            _open_multi -= 1
+            if _open_multi == 0:
+                lib.wotb_set_pdl(1)
+
 
 class Pipeline:
     def __init__(self, device=None, streams=2, make_stream=None, compute_slots=0):
@@ -35,12 +68,11 @@ class Pipeline:
         with the other contexts' solves."""
         if streams < 1:
             raise ValueError("streams must be >= 1")
-        _lib.load().wotb_set_compute_slots(int(compute_slots))
-        self._slots = int(compute_slots)
-        self._pdl_off = streams > 1
-        if self._pdl_off:
-            # programmatic dependent launch helps a lone solve and hurts interleaved ones (csrc/online_tc.cuh)
-            _lib.load().wotb_set_pdl(0)
+        self._slots = max(0, int(compute_slots))
+        # programmatic dependent launch helps a lone solve and hurts interleaved ones (csrc/online_tc.cuh)
+        self._multi = streams > 1
+        _settings_open(self._slots, self._multi)
+        self._settings_held = True
         if device is None:
             device = _lib.context().device
         self.device = int(device)
@@ -99,11 +131,9 @@ class Pipeline:
             else:
                 ctx.close()
         self.contexts = []
-        if self._slots:
-            _lib.load().wotb_set_compute_slots(0)
-        if self._pdl_off:
-            _lib.load().wotb_set_pdl(1)
-            self._pdl_off = False
+        if self._settings_held:
+            _settings_close(self._slots, self._multi)
+            self._settings_held = False
 
     def __enter__(self):
         return self
