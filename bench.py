@@ -23,10 +23,19 @@ day-pairs in flight on separate CUDA streams (wot_b200.pipeline; a step is still
             --kernel stored: k_fused, one Sinkhorn iteration streaming K once; bound = HBM, algorithmic bytes
             = 4*I*ld per launch, peak = MEASURED_PEAKS.json hbm_gbs.  The other variant's figures ride along
             as roofline_stored / roofline_online.
-  cpu_baseline  the float64 NumPy port of the reference (oracle/) on a bounded sample, host cores.
+  cpu_baseline  the UNMODIFIED reference solver (oracle/_ref, a byte-for-byte copy of wot/ot/optimal_transport.py made
+                by oracle/build_ref.py; the NumPy port in oracle/ if that copy is missing) on a bounded sample.
+  c3, c5        BASELINE.json configs[2] (50k x 50k, stored-K vs online-K) and a slice of configs[4] (sweep), N = 1.
+  e2e_api       the same workload through the PUBLIC model API from expression matrices:
+                OTModel(adata, growth_iters=3).compute_all_transport_maps -> local PCA on the GPU, cost, solves,
+                .h5ad files (first --api-pairs day-pairs).
+  row_sharded   N > 1: BASELINE.json configs[3], one 100k x 100k pair with its rows sharded over the N GPUs and an
+                NCCL all-reduce per Sinkhorn iteration; timing, all-reduce share and parity checks.
 
-`--impl reference` times that CPU port alone (the reference is pure Python and cannot travel to the GPU
-box; oracle/ is its line-by-line restatement, pinned to the reference by tests/golden).
+`--impl reference` times the reference's own CPU implementation of the path on the host cores: cost
+(sklearn pairwise_distances + np.median, ot_model.py:249-252) + compute_transport_matrix(optimal_transport_duality_gap,
+growth_iters=3) on atlas pairs AT FULL SIZE (the smallest one, and at N = 1 also the median one); the remaining pairs
+are extrapolated in proportion to I*J and the line says so.
 """
 import argparse
 import ctypes as C
@@ -111,66 +120,117 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU port of the reference (oracle/) -- bounded sample
+# the reference's CPU path
 # ------------------------------------------------------------------------------------------------
+def reference_module():
+    """(module, kind): the unmodified reference solver module from oracle/_ref ('reference'), else the NumPy port of
+    oracle/ ('port').  On the build container the copy is refreshed from /root/reference first."""
+    from oracle import build_ref
+    try:
+        build_ref.build()
+    except Exception:
+        pass
+    mod = build_ref.load()
+    if mod is not None:
+        return mod, "reference"
+    from oracle import wot_oracle
+    return wot_oracle, "port"
+
+
+def host_threads():
+    """Give BLAS every host core (torchrun exports OMP_NUM_THREADS=1, which would silently turn an N > 1 reference
+    arm into a single-threaded one) and return the number in use."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=n)
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return n
+
+
+def reference_tmap(mod, kind, x0, x1, growth, growth_iters):
+    """One transport map the way the reference computes it: ot_model.py:249-252 (cost) + :318 (growth loop)."""
+    import sklearn.metrics
+    t0 = time.perf_counter()
+    cost = sklearn.metrics.pairwise.pairwise_distances(x0, x1, metric="sqeuclidean", n_jobs=-1)
+    cost = cost / np.median(cost)
+    params = dict(DEFAULTS, growth_iters=growth_iters, C=cost, G=growth.copy())
+    if kind == "port":
+        params["gap"] = "dense"
+    tmap, _ = mod.compute_transport_matrix(mod.optimal_transport_duality_gap, **params)
+    return time.perf_counter() - t0, float(tmap.sum())
+
+
 def cpu_reference_sample(pair, cells, growth_iters=1):
-    """Full reference-port solve (dense primal/dual like the reference) of `pair` subsampled to `cells`
-    cells/day.  Returns (seconds, I, J, iters)."""
-    from oracle import wot_oracle as orc
+    """Full solve of `pair` subsampled to `cells` cells/day.  Returns (seconds, I, J, kind)."""
     from wot_b200 import synthetic
+    mod, kind = reference_module()
     n0, n1, seed = pair
     s = min(1.0, cells / max(n0, n1))
     m0, m1 = max(2, int(n0 * s)), max(2, int(n1 * s))
     x0, x1, growth = synthetic.day_pair_coords(m0, m1, d=D, seed=seed)
-    t0 = time.perf_counter()
-    cost = orc.compute_default_cost_matrix(x0, x1)
-    info = orc.SolveInfo()
-    params = dict(DEFAULTS, growth_iters=growth_iters, C=cost, G=growth.copy(), info=info, gap="dense")
-    orc.compute_transport_matrix(orc.optimal_transport_duality_gap, **params)
-    return time.perf_counter() - t0, m0, m1, info.iters
-
-
-def blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
-    except Exception:
-        return os.cpu_count() or 1
+    sec, _ = reference_tmap(mod, kind, x0, x1, growth, growth_iters)
+    return sec, m0, m1, kind
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU port on host cores.  Rank 0 alone works."""
+    """--impl reference: the reference's CPU path on the host cores.  Rank 0 alone works."""
     if rank != 0:
         return
     from wot_b200 import synthetic
+    cores = host_threads()
+    mod, kind = reference_module()
     pairs = synthetic.atlas_pairs(seed=1, scale=args.scale)
-    mean_ij = float(np.mean([a * b for a, b, _ in pairs]))
-    steps = max(1, min(args.steps, 6))
-    warm = min(args.warmup, 1)
-    cells = args.cpu_cells
-    per_entry = []
-    for s in range(warm + steps):
-        sec, m0, m1, iters = cpu_reference_sample(pairs[s % len(pairs)], cells, growth_iters=1)
-        if s >= warm:
-            per_entry.append(sec / (m0 * m1))
-    # one tmap of the workload = GROWTH_ITERS cold-start solves over I*J entries (time is proportional to
-    # I*J: SURVEY.md section 6, 1.4 us per entry per solve measured from 2k^2 to 10k^2)
-    sec_per_tmap = float(np.mean(per_entry)) * mean_ij * GROWTH_ITERS
-    value = 1.0 / sec_per_tmap
-    cores = blas_threads()
-    sample = ("%d timed full solves (cost + duality-gap solver with the reference's dense primal/dual) of atlas "
-              "pairs subsampled to <=%d cells/day, growth_iters=1; seconds per matrix entry scaled to the mean "
-              "atlas pair (I*J=%.3g) x growth_iters=3" % (steps, cells, mean_ij))
+    order = sorted(range(len(pairs)), key=lambda k: pairs[k][0] * pairs[k][1])
+    timed = [order[0]] + ([order[len(order) // 2]] if args.gpus == 1 and args.steps > 1 else [])
+    secs, entries = [], []
+    for k in timed:
+        n0, n1, seed = pairs[k]
+        x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=D, seed=seed)
+        sec, _ = reference_tmap(mod, kind, x0, x1, growth, GROWTH_ITERS)
+        secs.append(sec)
+        entries.append(n0 * n1)
+    # the 39-pair job: measured pairs as measured, every other pair at the measured seconds per matrix entry
+    per_entry = sum(secs) / sum(entries)
+    total = sum(secs[timed.index(k)] if k in timed else per_entry * pairs[k][0] * pairs[k][1] for k in range(len(pairs)))
+    value = len(pairs) / total
+    sample = ("%d atlas day-pair(s) at FULL size through the %s (%s) with growth_iters=3: %s; the other %d pairs of the "
+              "39-pair job are extrapolated at the measured %.3g us per matrix entry (time is proportional to I*J, "
+              "SURVEY.md section 6); BLAS threads %d, sklearn pairwise_distances n_jobs=-1"
+              % (len(timed), "unmodified reference solver" if kind == "reference" else "NumPy port of the reference",
+                 "oracle/_ref" if kind == "reference" else "oracle/",
+                 ", ".join("%dx%d in %.1f s" % (pairs[k][0], pairs[k][1], t) for k, t in zip(timed, secs)),
+                 len(pairs) - len(timed), 1e6 * per_entry, cores))
     line = {
         "impl": "reference", "metric": "day-pair transport maps per second", "value": value, "unit": "tmaps/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec_per_tmap,
+        "n_gpus": args.gpus, "steps": len(timed), "warmup": 0, "ms_per_step": 1e3 * sum(secs) / len(timed),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "solver": "duality_gap", "eps": 0.05, "lambda1": 1, "lambda2": 50},
-        "cpu_baseline": {"value": value, "unit": "tmaps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config("cpu", 1, args.scale),
+        "cpu_baseline": {"value": value, "unit": "tmaps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "tmaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "measured_pairs": [{"shape": [pairs[k][0], pairs[k][1]], "seconds": t} for k, t in zip(timed, secs)],
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def bench_config(kernel, streams, scale):
+    """The `config` object: identical keys in both arms; the values that describe the GPU launch mode are null on the
+    CPU arm."""
+    gpu = kernel != "cpu"
+    online = gpu and kernel != "stored"
+    return {
+        "workload": WORKLOAD, "solver": "duality_gap", "eps": 0.05, "lambda1": 1, "lambda2": 50, "growth_iters": GROWTH_ITERS,
+        "scale": scale, "kernel": kernel if gpu else None, "streams": streams if gpu else None,
+        "l2": (("every pass recomputes I*J = 25M-400M entries from L2-resident operands; nothing is cached between steps "
+                "(each step is a different day-pair)") if online else
+               "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)") if gpu else None,
+        "sharding": "one day-pair per GPU per step, no collective",
+        "streams_note": ("day-pairs are independent: each GPU keeps `streams` of them in flight on separate CUDA streams "
+                         "(wot_b200.pipeline) so one fills the other's kernel tails, checks and copies; a step is still "
+                         "one day-pair") if gpu else None,
+    }
 
 
 # ------------------------------------------------------------------------------------------------

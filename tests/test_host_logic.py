@@ -141,10 +141,13 @@ def test_kernel_policy_and_day_slices():
     from wot_b200.ot import optimal_transport as wot_ot
     from wot_b200.ot.ot_model import _rows_key
     assert wot_ot.resolve_kernel("auto", 1000, 1000, 30, 0.05) == "online"
-    assert wot_ot.resolve_kernel("auto", 1000, 1000, 30, 0.01) == "stored"      # exponent error grows like 1/eps
+    assert wot_ot.resolve_kernel("auto", 1000, 1000, 30, 0.01) == "online"      # precise operands below eps 0.02
     assert wot_ot.resolve_kernel("auto", 1000, 1000, 47, 0.05) == "stored"      # beyond the tcgen05 K budget
     assert wot_ot.resolve_kernel("stored", 1000, 1000, 30, 0.05) == "stored"
-    assert wot_ot._kernel_id("online_simt") == (wot_ot._lib.KERNEL_ONLINE, True)
+    assert wot_ot._kernel_id("online_simt") == (wot_ot._lib.KERNEL_ONLINE, True, None)
+    assert wot_ot._kernel_id("online_precise") == (wot_ot._lib.KERNEL_ONLINE, False, True)
+    assert wot_ot._lib.make_params(online_precise=True).reserved & 4
+    assert wot_ot._lib.make_params(online_precise=False).reserved & 8
     with pytest.raises(ValueError):
         wot_ot._kernel_id("fast")
     mask = np.array([False, True, True, True, False])
@@ -158,3 +161,45 @@ def test_cli_additive_flags():
     from wot_b200.commands import optimal_transport as cli
     args = cli.create_parser().parse_args(["--matrix", "m.txt", "--cell_days", "d.txt", "--streams", "3", "--kernel", "auto"])
     assert args.streams == 3 and args.kernel == "auto" and args.format == "h5ad" and args.out == "./tmaps"
+
+
+def test_pinned_block_lives_as_long_as_any_view():
+    """A pooled page-locked block goes back to the pool only when the LAST array viewing it is gone, including the
+    plain-ndarray views NumPy derives (np.asarray, slices, DataFrame): a second solve must not overwrite a map the
+    caller still holds."""
+    import ctypes
+    import gc
+
+    import pandas as pd
+    from wot_b200 import _pinned
+
+    class Block:
+        def __init__(self, n):
+            self.nbytes, self.buf = n, (ctypes.c_char * n)()
+
+    made = []
+
+    def alloc(n):
+        made.append(Block(n))
+        return made[-1]
+
+    old_alloc, old_free = _pinned._alloc, list(_pinned._free)
+    _pinned._alloc, _pinned._free[:] = alloc, []
+    try:
+        a = _pinned.empty((4, 5), np.float64)
+        a[...] = 1.5
+        plain, part, frame = np.asarray(a), a[1:3], pd.DataFrame(a)
+        del a
+        gc.collect()
+        assert len(_pinned._free) == 0                     # still viewed
+        b = _pinned.empty((4, 5), np.float64)              # the "second solve": must get a different block
+        b[...] = 7.0
+        assert len(made) == 2 and plain[0, 0] == 1.5 and part[0, 0] == 1.5 and frame.iloc[3, 4] == 1.5
+        del plain, part, frame
+        gc.collect()
+        assert len(_pinned._free) == 1                     # now recycled
+        c = _pinned.empty((2, 2), np.float64)
+        assert len(made) == 2                              # served from the pool
+        del b, c
+    finally:
+        _pinned._alloc, _pinned._free[:] = old_alloc, old_free

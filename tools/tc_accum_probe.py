@@ -28,7 +28,7 @@ def run(ctx, torch, x_out, x_in, off_out, off_in, impl=2):
     return sums.cpu().numpy()
 
 
-def case(ctx, torch, rng, n, d, amp, q, grid, dims_active=None):
+def case(ctx, torch, rng, n, d, amp, q, grid, dims_active=None, impl=2, by_target=False):
     scale = 2.0 ** q
     x = rng.uniform(-amp, amp, size=(n, d))
     y = rng.uniform(-amp, amp, size=(1, d))
@@ -39,18 +39,26 @@ def case(ctx, torch, rng, n, d, amp, q, grid, dims_active=None):
         x = np.rint(x * scale) / scale
         y = np.rint(y * scale) / scale
     dot = (x * y).sum(1)                       # exact in float64 for grid inputs (multiples of 2^-2q, < 2^30)
-    target = -rng.integers(1, 12, size=n).astype(np.float64)
+    target = -rng.integers(1, 30, size=n).astype(np.float64) if by_target else -rng.integers(1, 12, size=n).astype(np.float64)
+    if by_target and not grid:
+        target = target + rng.uniform(-0.5, 0.5, size=n)
     q_off = -np.floor(0.5 * (y * y).sum())     # integer
     p_off = target - dot - q_off
     if grid:
         # make P a multiple of 2^-2q (it is, since dot is) and check representability by the two fp16 slots
         assert np.all(np.abs(p_off * 4.0 ** q - np.rint(p_off * 4.0 ** q)) < 1e-9)
-    got = run(ctx, torch, x, y, p_off, np.array([q_off]))
+    got = run(ctx, torch, x, y, p_off, np.array([q_off]), impl=impl)
     err = np.log2(got) - target
     part = np.abs(dot).max()
     print("%-5s q=%d amp=%5.1f d_active=%2s  |<X,Y>|max %7.1f |P|max %7.1f  err: mean %+.3e  rms %.3e  max %.3e  exact rows %d/%d"
           % ("grid" if grid else "float", q, amp, dims_active or d, part, np.abs(p_off).max(), err.mean(),
              np.sqrt((err ** 2).mean()), np.abs(err).max(), int((err == 0).sum()), n), flush=True)
+    if by_target:
+        for lo, hi in ((0, 2), (2, 4), (4, 8), (8, 16), (16, 32)):
+            sel = (-target >= lo) & (-target < hi)
+            if sel.any():
+                print("        impl %d  |D| in [%2d,%2d): n %5d  mean %+.3e  rms %.3e" % (impl, lo, hi, int(sel.sum()), err[sel].mean(),
+                                                                                 np.sqrt((err[sel] ** 2).mean())), flush=True)
 
 
 def main():
@@ -62,6 +70,10 @@ def main():
         case(ctx, torch, rng, n, d, amp, q, True)
     for amp in (3.0, 6.0, 12.0, 24.0):
         case(ctx, torch, rng, n, d, amp, 0, False)
+    # error of the exponent by its magnitude, default vs precise operands, at magnitudes of eps = 0.05 / 0.01 / 0.005
+    for amp in (3.0, 6.0, 9.0):
+        for impl in (2, 3):
+            case(ctx, torch, rng, 16384, d, amp, 0, False, impl=impl, by_target=True)
     # few active dimensions: products large relative to the sum
     for amp, q in ((12.0, 6), (24.0, 5)):
         case(ctx, torch, rng, n, d, amp, q, True, dims_active=4)

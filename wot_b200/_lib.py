@@ -129,7 +129,7 @@ def check(rc):
 
 def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tolerance=1e-8, max_iter=1e7,
                 batch_size=5, scaling_iter=3000, extra_iter=1000, inner_iter_max=50, solver=SOLVER_DUALITY_GAP,
-                kernel=KERNEL_STORED, use_graph=True, fuse=True, online_simt=False, **ignored):
+                kernel=KERNEL_STORED, use_graph=True, fuse=True, online_simt=False, online_precise=None, **ignored):
     """Pack the ot_config keys the solvers read (ot_model.py:85-87).  Unknown keys are ignored, like the
     reference solvers' **ignored."""
     p = Params()
@@ -139,8 +139,11 @@ def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tole
     p.batch_size, p.scaling_iter = int(batch_size), int(scaling_iter)
     p.extra_iter, p.inner_iter_max = int(extra_iter), int(inner_iter_max)
     p.solver, p.kernel, p.use_graph = int(solver), int(kernel), int(bool(use_graph))
-    # bit0: disable the fused (K-read-once) iteration kernel; bit1: online kernel on the SIMT FP32 pass, not tcgen05
+    # bit0: disable the fused (K-read-once) iteration kernel; bit1: online kernel on the SIMT FP32 pass, not tcgen05;
+    # bit2 / bit3: force / forbid the precise 6-segment operands of the tcgen05 pass (default: by final epsilon)
     p.reserved = (0 if fuse else 1) | (2 if online_simt else 0)
+    if online_precise is not None:
+        p.reserved |= 4 if online_precise else 8
     return p
 
 

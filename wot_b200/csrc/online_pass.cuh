@@ -80,13 +80,70 @@ __device__ __forceinline__ void tc_split(double x, __half &hi, __half &lo) {
     lo = __double2half((x - (double)__half2float(hi)) * 2048.0);
 }
 
-// offset `value` of in-side row `idx` into its two slots (b1 | . | b2'), see online_tc.cuh
-__device__ __forceinline__ void tc_store_in_offset(__half *opB, long long idx, double value, int kseg) {
-    const int kc = 3 * (kseg >> 3);
-    __half b1, b2;
-    tc_split(fmax(value, (double)kTcPad), b1, b2);
-    opB[tc_index(idx, kseg - 2, kc)] = b1;
-    opB[tc_index(idx, 3 * kseg - 2, kc)] = b2;
+// ---- precise operand mode (6 segments, online_tc.cuh): three 11-bit limbs per coordinate, the leading one on a
+// fixed-point grid 2^-q so that the large cancelling part of the exponent accumulates EXACTLY in the fp32 TMEM
+// accumulator (measured on B200, profiles/r2b_tc_accum_probe.txt: operands that share a quantum give bit-exact
+// sums).  `TcGeo` holds what the grid choice needs, reduced once per solve from the coordinates.
+struct TcGeo {
+    double max_abs;   // max |x_ik| over both sides and all dimensions
+    double max_n2x;   // max |x_i|^2
+    double max_n2y;   // max |y_j|^2
+};
+
+// fractional bits of the leading limb for coordinates scaled by sc: the limb must fit fp16's 11 bits, and every
+// partial sum of the leading segment (|<X,Y>| + |integer offsets|) must stay below 2^24 quanta of 2^-2q
+__host__ __device__ __forceinline__ int tc_grid_q(double sc, const TcGeo &g) {
+    int ib = 0;
+    frexp(sc * g.max_abs * 1.0000001 + 1e-300, &ib);  // sc * max_abs < 2^ib
+    if (ib < 0) ib = 0;
+    const int q1 = 10 - ib;
+    const double n2 = g.max_n2x > g.max_n2y ? g.max_n2x : g.max_n2y;
+    int eb = 0;
+    frexp(2.0 * sc * sc * n2 + 1024.0, &eb);          // bound < 2^eb
+    const int q2 = (23 - eb) / 2;
+    int q = q1 < q2 ? q1 : q2;
+    if (q > 8) q = 8;                                  // h * 2^-(q+7) must stay a multiple of 2^-24 (fp16 subnormal step)
+    if (q < 0) q = 0;
+    return q;
+}
+
+// The fp32 accumulator of tcgen05.mma rounds TOWARD ZERO once per instruction: after the two exact instructions of
+// the leading segment the ten that follow each cost the running exponent D half an ulp on average, i.e.
+// D_computed = D (1 - kappa) with kappa = 3.1e-7, measured on B200 independent of the operand magnitudes
+// (profiles/r2d_tc_accum_bias_by_magnitude.txt: mean error of log2 = 3.1e-7 |D| in every binade of |D|).  An error
+// proportional to D is removed by presenting D (1 + kappa) to the tensor core: coordinates are scaled by
+// sqrt(1 + kappa) and offsets by (1 + kappa) before they are split.  What remains is zero-mean.
+constexpr double kTcTruncComp = 3.1e-7;
+
+// offset = o1 + o2 + 2^-11 o3' (+ residual): o1 an integer (exact in the leading segment), o2 the fraction to fp16
+// precision, o3' the next 11 bits
+__device__ __forceinline__ double tc_split3(double value, __half &o1, __half &o2, __half &o3) {
+    o1 = __double2half(rint(value));
+    double r = value - (double)__half2float(o1);
+    o2 = __double2half(r);
+    r -= (double)__half2float(o2);
+    o3 = __double2half(r * 2048.0);
+    return r - (double)__half2float(o3) * (1.0 / 2048.0);
+}
+
+// offset `value` of in-side row `idx` into its slots (b1 | . | b2') of the 3-segment layout or (b1 | b2 | b3' | ...)
+// of the 6-segment layout, see online_tc.cuh
+__device__ __forceinline__ void tc_store_in_offset(__half *opB, long long idx, double value, int kseg, int nseg) {
+    const int kc = nseg * (kseg >> 3);
+    if (nseg == 3) {
+        value = fmax(value, (double)kTcPad);
+        __half b1, b2;
+        tc_split(value, b1, b2);
+        opB[tc_index(idx, kseg - 2, kc)] = b1;
+        opB[tc_index(idx, 3 * kseg - 2, kc)] = b2;
+    } else {
+        value = fmax(value * (1.0 + kTcTruncComp), (double)kTcPad);
+        __half b1, b2, b3;
+        tc_split3(value, b1, b2, b3);
+        opB[tc_index(idx, kseg - 2, kc)] = b1;
+        opB[tc_index(idx, 2 * kseg - 2, kc)] = b2;
+        opB[tc_index(idx, 3 * kseg - 2, kc)] = b3;
+    }
 }
 
 // What a finished out entry does with its reduced sum s (shared by the SIMT and the tcgen05 pass kernels).
@@ -104,14 +161,14 @@ __device__ __forceinline__ double online_apply(int mode, int o, double s, const 
             V.s[o] = s;
             if (ctrl->batch_done == 0) V.sfirst[o] = s;
             V.Pd[o] = (ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
-            if (V.tcXB) tc_store_in_offset(V.tcXB, o, V.Pd[o], V.tc_kseg);
+            if (V.tcXB) tc_store_in_offset(V.tcXB, o, V.Pd[o], V.tc_kseg, V.tc_nseg);
             vmax = fabs(a);
         } else {
             const double b = scaling_update(ctrl->lq, s, ctrl->alpha2, V.lv[o]);
             V.b[cur ^ 1][o] = b;
             V.t[o] = s;
             V.Qd[o] = (ctrl->c1 * V.v[o] - ctrl->c2 * V.ny[o] + log2(b) - log2((double)J));
-            if (V.tcYB) tc_store_in_offset(V.tcYB, o, V.Qd[o], V.tc_kseg);
+            if (V.tcYB) tc_store_in_offset(V.tcYB, o, V.Qd[o], V.tc_kseg, V.tc_nseg);
             vmax = fabs(b);
         }
     } else if (mode == 1) {

@@ -29,12 +29,14 @@ struct OnlinePasses {
     TcPlan plan;
     __half *XA = nullptr, *XB = nullptr, *YA = nullptr, *YB = nullptr;
     double *resid_x = nullptr, *resid_y = nullptr;
+    TcGeo *geo = nullptr;
     TcArgs trow, tcol;
     int tgrid_row = 0, tgrid_col = 0;
     bool have_rows = true;
 
-    int setup(wotb_ctx *c, const double *x0_, int64_t I_, const double *x1_, int64_t J_, int d_, bool want_tc, int shard,
-              int n_shards, SolveVecs *V, cudaStream_t st) {
+    // precise: 6-segment operands (exact accumulation of the large cancelling terms), for small final epsilon
+    int setup(wotb_ctx *c, const double *x0_, int64_t I_, const double *x1_, int64_t J_, int d_, bool want_tc, bool precise,
+              int shard, int n_shards, SolveVecs *V, cudaStream_t st) {
         ctx = c, x0 = x0_, x1 = x1_, I = I_, J = J_, d = d_;
         tc = want_tc && tc_supported(d);
         ldi = round_up(I, kTcOut), ldj = round_up(J, kTcOut);
@@ -59,13 +61,13 @@ struct OnlinePasses {
         const size_t o_pd = take((size_t)ldi * 8), o_qd = take((size_t)ldj * 8);
         const size_t o_p0 = take((size_t)ldi * 8), o_q0 = take((size_t)ldj * 8);
         const size_t o_cnt = take((size_t)(ldi + ldj) / kOnTile * 4 + 64);
-        size_t o_xt = 0, o_yt = 0, o_part = 0, o_xa = 0, o_xb = 0, o_ya = 0, o_yb = 0, o_rx = 0, o_ry = 0;
+        size_t o_xt = 0, o_yt = 0, o_part = 0, o_xa = 0, o_xb = 0, o_ya = 0, o_yb = 0, o_rx = 0, o_ry = 0, o_geo = 0;
         int nseg_row = 1, nseg_col = 1, seg_tiles_row = 1, seg_tiles_col = 1, slots_row = 1, slots_col = 1;
         if (tc) {
-            plan = tc_plan(d, 8);
-            const size_t row_bytes = (size_t)plan.kseg * 6;
+            plan = tc_plan(d, 8, precise ? 6 : 3);
+            const size_t row_bytes = plan.row_bytes();
             o_xa = take(ldi * row_bytes), o_xb = take(ldi * row_bytes), o_ya = take(ldj * row_bytes), o_yb = take(ldj * row_bytes);
-            o_rx = take(ldi * 8), o_ry = take(ldj * 8);
+            o_rx = take(ldi * 8), o_ry = take(ldj * 8), o_geo = take(sizeof(TcGeo));
             tgrid_row = tc_grid(ctx->sm_count, my_blocks > 0 ? my_blocks : 1, tiles_j, &slots_row);
             tgrid_col = tc_grid(ctx->sm_count, blocks_j, my_tiles > 0 ? my_tiles : 1, &slots_col);
             o_part = take((size_t)(slots_row > slots_col ? slots_row : slots_col) * (ldi > ldj ? ldi : ldj) * 8);
@@ -101,7 +103,11 @@ struct OnlinePasses {
             WOTB_TRY(tc_configure(plan));
             XA = (__half *)(ob + o_xa), XB = (__half *)(ob + o_xb), YA = (__half *)(ob + o_ya), YB = (__half *)(ob + o_yb);
             resid_x = (double *)(ob + o_rx), resid_y = (double *)(ob + o_ry);
-            V->tcXB = XB, V->tcYB = YB, V->tc_kseg = plan.kseg;
+            V->tcXB = XB, V->tcYB = YB, V->tc_kseg = plan.kseg, V->tc_nseg = plan.nseg;
+            geo = (TcGeo *)(ob + o_geo);
+            WOTB_CUDA(cudaMemsetAsync(geo, 0, sizeof(TcGeo), st));
+            k_tc_geo<<<(unsigned)cdiv(I, 256), 256, 0, st>>>(x0, (int)I, d, geo, 0);
+            k_tc_geo<<<(unsigned)cdiv(J, 256), 256, 0, st>>>(x1, (int)J, d, geo, 1);
             trow.opA = XA, trow.opB = YB, trow.resid = resid_x, trow.out_n = (int)I, trow.out_ld = ldi;
             trow.n_blocks = my_blocks, trow.out_blk0 = b_lo, trow.in_tile0 = 0, trow.in_ntiles = tiles_j;
             trow.n_stages = plan.n_stages, trow.part = part, trow.counters = cnt_i, trow.dbg = 0, trow.prof = nullptr;
@@ -133,8 +139,8 @@ struct OnlinePasses {
     int pack(cudaStream_t st, SolveCtrl *c) const {
         if (tc) {
             const int cps = plan.kseg / 8;
-            k_tc_pack<<<(unsigned)cdiv(ldi * cps, 256), 256, 0, st>>>(x0, (int)I, d, ldi, plan.kseg, XA, XB, c, 0.0);
-            k_tc_pack<<<(unsigned)cdiv(ldj * cps, 256), 256, 0, st>>>(x1, (int)J, d, ldj, plan.kseg, YA, YB, c, 0.0);
+            k_tc_pack<<<(unsigned)cdiv(ldi * cps, 256), 256, 0, st>>>(x0, (int)I, d, ldi, plan.kseg, plan.nseg, XA, XB, c, 0.0, geo);
+            k_tc_pack<<<(unsigned)cdiv(ldj * cps, 256), 256, 0, st>>>(x1, (int)J, d, ldj, plan.kseg, plan.nseg, YA, YB, c, 0.0, geo);
         } else {
             k_online_scale<<<(unsigned)cdiv((int64_t)dp * ldi, 256), 256, 0, st>>>(x0, (int)I, d, XT, ldi, dp, c, 0);
             k_online_scale<<<(unsigned)cdiv((int64_t)dp * ldj, 256), 256, 0, st>>>(x1, (int)J, d, YT, ldj, dp, c, 0);
@@ -146,7 +152,7 @@ struct OnlinePasses {
         const unsigned nb = (unsigned)cdiv(ldi > ldj ? ldi : ldj, 256);
         k_online_s0_offsets<<<nb, 256, 0, st>>>(V, c, P0, Q0);
         if (tc) {
-            k_tc_slots<<<nb, 256, 0, st>>>(P0, (int)I, XA, resid_x, Q0, (int)J, YB, plan.kseg, c, 3);
+            k_tc_slots<<<nb, 256, 0, st>>>(P0, (int)I, XA, resid_x, Q0, (int)J, YB, plan.kseg, plan.nseg, c, 3);
             if (have_rows) tc_launch<false>(plan, tgrid_row, st, trow, V, c, 3, nullptr);
             return 3;
         }
@@ -161,8 +167,8 @@ struct OnlinePasses {
     int refresh_slots(cudaStream_t st, const SolveVecs &V, SolveCtrl *c, int gate) const {
         if (!tc) return 0;
         const unsigned nb = (unsigned)cdiv(ldi > ldj ? ldi : ldj, 256);
-        k_tc_slots<<<nb, 256, 0, st>>>(V.Ps, (int)I, XA, resid_x, V.Qd, (int)J, YB, plan.kseg, c, gate);
-        k_tc_slots<<<nb, 256, 0, st>>>(V.Qs, (int)J, YA, resid_y, V.Pd, (int)I, XB, plan.kseg, c, gate);
+        k_tc_slots<<<nb, 256, 0, st>>>(V.Ps, (int)I, XA, resid_x, V.Qd, (int)J, YB, plan.kseg, plan.nseg, c, gate);
+        k_tc_slots<<<nb, 256, 0, st>>>(V.Qs, (int)J, YA, resid_y, V.Pd, (int)I, XB, plan.kseg, plan.nseg, c, gate);
         return 2;
     }
     void row_pass(cudaStream_t st, const SolveVecs &V, SolveCtrl *c, int mode, double *out) const {
@@ -180,6 +186,19 @@ struct OnlinePasses {
             k_online_pass<true><<<grid_col, kOnThreads, smem, st>>>(col, V, c, mode, out);
     }
 };
+
+// Operand mode of the tcgen05 pass.  The default fp16 hi/lo operands accumulate the exponent with an error of about
+// 5e-7 / eps that is mostly a truncation BIAS of the fp32 accumulator at the magnitude of the cancelling terms
+// (profiles/r2a_online_pass_accuracy_vs_eps.txt: -4.4e-6 at eps 0.01, -1.1e-5 at 0.005); slowly converging settings
+// are sensitive to such a systematic perturbation of K and end a few batches away from the reference.  Below a
+// final epsilon of 0.02 (or when params->reserved bit2 asks for it; bit3 forbids it) the precise 6-segment
+// operands are used: error ~1e-6 whatever epsilon, at about twice the tensor-core work.
+inline bool online_precise(const wotb_params *prm) {
+    if (prm->reserved & 8) return false;
+    if (prm->reserved & 4) return true;
+    const double eps_final = prm->solver == WOTB_SOLVER_DUALITY_GAP ? prm->epsilon * prm->epsilon0 : prm->epsilon;
+    return eps_final < 0.02;
+}
 
 int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
                          const double *G, const wotb_params *prm, double *f, double *g, double *rowsum,
@@ -202,7 +221,7 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
 
     WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
     OnlinePasses P;
-    WOTB_TRY(P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), 0, 1, &V, st));
+    WOTB_TRY(P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), online_precise(prm), 0, 1, &V, st));
     WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     launch_init(ctx, V, d_ctrl, round_up(J, 32));
 
@@ -289,7 +308,7 @@ __global__ void k_import_a(SolveVecs V, SolveCtrl *ctrl, const double *__restric
         V.a[ctrl->cur ^ 1][i] = a;
         if (ctrl->batch_done == 0) V.sfirst[i] = src[I + i];
         V.Pd[i] = (ctrl->c1 * V.u[i] - ctrl->c2 * V.nx[i] + log2(a) - log2((double)I));
-        if (V.tcXB) tc_store_in_offset(V.tcXB, i, V.Pd[i], V.tc_kseg);
+        if (V.tcXB) tc_store_in_offset(V.tcXB, i, V.Pd[i], V.tc_kseg, V.tc_nseg);
         vmax = fabs(a);
     }
     vmax = warp_max(vmax);
@@ -317,7 +336,7 @@ __global__ void k_online_col_finish(SolveVecs V, SolveCtrl *ctrl, const double *
         V.b[cur ^ 1][j] = b;
         V.t[j] = t;
         V.Qd[j] = (ctrl->c1 * V.v[j] - ctrl->c2 * V.ny[j] + log2(b) - log2((double)J));
-        if (V.tcYB) tc_store_in_offset(V.tcYB, j, V.Qd[j], V.tc_kseg);
+        if (V.tcYB) tc_store_in_offset(V.tcYB, j, V.Qd[j], V.tc_kseg, V.tc_nseg);
         vmax = fabs(b);
     }
     vmax = warp_max(vmax);
@@ -356,7 +375,8 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     if (rc == WOTB_OK && cudaSetDevice(ctx->device) != cudaSuccess) rc = WOTB_ERR_CUDA;
     cudaStream_t st = ctx->stream;
     if (rc == WOTB_OK) rc = carve_vectors(ctx, I, J, round_up(J, 32), 1, 1, (int)I, G, f, g, &S->V);
-    if (rc == WOTB_OK) rc = S->P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), shard, n_shards, &S->V, st);
+    if (rc == WOTB_OK)
+        rc = S->P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), online_precise(prm), shard, n_shards, &S->V, st);
     if (rc == WOTB_OK) rc = ctx->ctrl.reserve(sizeof(SolveCtrl));
     if (rc == WOTB_OK) rc = ctx->status.reserve(256);
     if (rc != WOTB_OK) {

@@ -58,8 +58,19 @@ constexpr int kTcSmemLimit = 232448;
 // ---- operand preparation ------------------------------------------------------------------------
 // Coordinates (scaled for the current epsilon) into both operand roles of one side.
 // The online analogue of rebuilding K (optimal_transport.py:124,:140): runs when need_build is set.
-__global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long rows_pad, int kseg,
-                          __half *__restrict__ opA, __half *__restrict__ opB, const SolveCtrl *ctrl, double scale) {
+//
+// nseg == 3 (default): x = hi + 2^-11 lo' with hi = fp16(x):   A [ hi | lo' | hs ]   B [ hi | hs | lo' ],  hs = 2^-11 hi.
+// nseg == 6 (precise): x = h + m + l, h = rint(x 2^q) 2^-q on the grid of tc_grid_q, m' = fp16((x - h) 2^(q+1)),
+//   l' = fp16((x - h - m) 2^(q+13)), all three limbs of 11 bits:
+//       A [ h | m' | h 2^-(q+1) | m'           | l' 2^-6     | h 2^-(q+7) ]
+//       B [ h | h 2^-(q+1) | m' | m' 2^-(2q+2) | h 2^-(q+7) | l' 2^-6     ]
+//   = h.h + m.h + h.m + m.m + l.h + h.l; the dropped m.l, l.l terms are below 2^-(2q+14) |x| per dimension.  The
+//   leading segment (with the integer parts of both offsets in its two spare slots) is a sum of multiples of
+//   2^-2q below 2^24 quanta: exact in the fp32 accumulator, so the cancellation of the large terms c2 |x|^2,
+//   c2 |y|^2, 2 c2 <x, y> costs nothing, and the remaining segments add small numbers to a small number.
+__global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long rows_pad, int kseg, int nseg,
+                          __half *__restrict__ opA, __half *__restrict__ opB, const SolveCtrl *ctrl, double scale,
+                          const TcGeo *__restrict__ geo) {
     if (ctrl && (ctrl->done || !ctrl->need_build)) return;
     const double sc = ctrl ? sqrt(2.0 * ctrl->c2) : scale;
     const int cps = kseg >> 3;  // 16-byte chunks per segment
@@ -68,34 +79,80 @@ __global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long 
     const int r_lo = (int)(idx & 7);
     const int c = (int)((idx >> 3) % cps);
     const long long r = (idx / (8 * cps)) * 8 + r_lo;
-    __align__(16) __half hi[8], lo[8], hs[8];
-    __align__(16) __half bhi[8], blo[8], bhs[8];
     const __half zero = __float2half(0.f), one = __float2half(1.f), tiny = __float2half(kTcLoInv);
+    const int kc = nseg * cps;
+    if (nseg == 3) {
+        __align__(16) __half hi[8], lo[8], hs[8];
+        __align__(16) __half bhi[8], blo[8], bhs[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = 8 * c + e;
+            double val = 0.0;
+            if (r < n && k < d) val = sc * x[r * d + k];
+            tc_split(val, hi[e], lo[e]);
+            hs[e] = __float2half(__half2float(hi[e]) * kTcLoInv);
+            bhi[e] = hi[e], blo[e] = lo[e], bhs[e] = hs[e];
+            if (k == kseg - 2) {
+                // A: (1 | 0 | 2^-11) picks up b1 and b2';  B: (b1 | 0 | b2') set by k_tc_slots, padding rows stay at kTcPad
+                hi[e] = one, lo[e] = zero, hs[e] = tiny;
+                bhi[e] = r < n ? zero : __float2half(kTcPad), bhs[e] = zero, blo[e] = zero;
+            } else if (k == kseg - 1) {
+                // A: (a1 | a2' | 0) set by k_tc_slots;  B: (1 | 2^-11 | 0) picks up a1 and a2'
+                hi[e] = zero, lo[e] = zero, hs[e] = zero;
+                bhi[e] = one, bhs[e] = tiny, blo[e] = zero;
+            }
+        }
+        *reinterpret_cast<uint4 *>(opA + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hi);
+        *reinterpret_cast<uint4 *>(opA + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(lo);
+        *reinterpret_cast<uint4 *>(opA + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hs);
+        *reinterpret_cast<uint4 *>(opB + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhi);
+        *reinterpret_cast<uint4 *>(opB + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhs);
+        *reinterpret_cast<uint4 *>(opB + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(blo);
+        return;
+    }
+    const int q = tc_grid_q(sc, *geo);
+    const double up = ldexp(1.0, q), dn = ldexp(1.0, -q);
+    const double scc = sc * sqrt(1.0 + kTcTruncComp);  // truncation compensation, see kTcTruncComp
+    __align__(16) __half sa[6][8], sb[6][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = 8 * c + e;
         double val = 0.0;
-        if (r < n && k < d) val = sc * x[r * d + k];
-        tc_split(val, hi[e], lo[e]);
-        hs[e] = __float2half(__half2float(hi[e]) * kTcLoInv);
-        bhi[e] = hi[e], blo[e] = lo[e], bhs[e] = hs[e];
+        if (r < n && k < d) val = scc * x[r * d + k];
+        const double h = rint(val * up) * dn;
+        const double r1 = val - h;
+        const __half mh = __double2half(ldexp(r1, q + 1));
+        const double m = ldexp((double)__half2float(mh), -(q + 1));
+        const __half lh = __double2half(ldexp(r1 - m, q + 13));
+        const __half hh = __double2half(h);                              // exact: |h| 2^q < 2^10
+        const __half h1 = __double2half(ldexp(h, -(q + 1)));             // exact (multiples of 2^-(2q+1) >= 2^-24)
+        const __half h7 = __double2half(ldexp(h, -(q + 7)));             // exact for q <= 8
+        const __half m2 = __double2half(ldexp((double)__half2float(mh), -(2 * q + 2)));
+        const __half l6 = __double2half(ldexp((double)__half2float(lh), -6));
+        sa[0][e] = hh, sb[0][e] = hh;
+        sa[1][e] = mh, sb[1][e] = h1;
+        sa[2][e] = h1, sb[2][e] = mh;
+        sa[3][e] = mh, sb[3][e] = m2;
+        sa[4][e] = l6, sb[4][e] = h7;
+        sa[5][e] = h7, sb[5][e] = l6;
         if (k == kseg - 2) {
-            // A: (1 | 0 | 2^-11) picks up b1 and b2';  B: (b1 | 0 | b2') set by k_tc_slots, padding rows stay at kTcPad
-            hi[e] = one, lo[e] = zero, hs[e] = tiny;
-            bhi[e] = r < n ? zero : __float2half(kTcPad), bhs[e] = zero, blo[e] = zero;
+            // in-side offsets b1 (integer) | b2 | b3': A holds the multipliers, B the values (k_tc_slots / finishing code)
+#pragma unroll
+            for (int sg = 0; sg < 6; ++sg) sa[sg][e] = zero, sb[sg][e] = zero;
+            sa[0][e] = one, sa[1][e] = one, sa[2][e] = tiny;
+            if (r >= n) sb[0][e] = __float2half(kTcPad);
         } else if (k == kseg - 1) {
-            // A: (a1 | a2' | 0) set by k_tc_slots;  B: (1 | 2^-11 | 0) picks up a1 and a2'
-            hi[e] = zero, lo[e] = zero, hs[e] = zero;
-            bhi[e] = one, bhs[e] = tiny, blo[e] = zero;
+            // out-side offsets a1 | a2 | a3': A holds the values, B the multipliers
+#pragma unroll
+            for (int sg = 0; sg < 6; ++sg) sa[sg][e] = zero, sb[sg][e] = zero;
+            sb[0][e] = one, sb[1][e] = one, sb[2][e] = tiny;
         }
     }
-    const int kc = 3 * cps;
-    *reinterpret_cast<uint4 *>(opA + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hi);
-    *reinterpret_cast<uint4 *>(opA + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(lo);
-    *reinterpret_cast<uint4 *>(opA + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(hs);
-    *reinterpret_cast<uint4 *>(opB + tc_index(r, 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhi);
-    *reinterpret_cast<uint4 *>(opB + tc_index(r, kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(bhs);
-    *reinterpret_cast<uint4 *>(opB + tc_index(r, 2 * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(blo);
+#pragma unroll
+    for (int sg = 0; sg < 6; ++sg) {
+        *reinterpret_cast<uint4 *>(opA + tc_index(r, sg * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(sa[sg]);
+        *reinterpret_cast<uint4 *>(opB + tc_index(r, sg * kseg + 8 * c, kc)) = *reinterpret_cast<const uint4 *>(sb[sg]);
+    }
 }
 
 // Exponent offsets into the spare K slots: the out side's static offsets into its A-role rows (+ the
@@ -103,7 +160,7 @@ __global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long 
 // slots are kept current by the finishing code (tc_store_in_offset); this kernel runs when everything changed.
 __global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half *__restrict__ opA_out,
                            double *__restrict__ resid, const double *__restrict__ off_in, int n_in,
-                           __half *__restrict__ opB_in, int kseg, const SolveCtrl *ctrl, int gate) {
+                           __half *__restrict__ opB_in, int kseg, int nseg, const SolveCtrl *ctrl, int gate) {
     // gate 0: unless the solve is done; 1: only when need_build is set (the offsets were rewritten by an absorption,
     // an epsilon change or the initialisation); 3: only for the S0 pass of the final stage; -1: always
     if (ctrl && gate >= 0) {
@@ -113,21 +170,44 @@ __global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half
             return;
     }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int kc = 3 * (kseg >> 3);
+    const int kc = nseg * (kseg >> 3);
     if (i < n_out) {
         const double al = fmax(off_out[i], (double)kTcPad);
-        __half a1, a2;
-        tc_split(al, a1, a2);
-        resid[i] = al - (double)__half2float(a1) - (double)__half2float(a2) * (double)kTcLoInv;
-        opA_out[tc_index(i, kseg - 1, kc)] = a1;
-        opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
+        if (nseg == 3) {
+            __half a1, a2;
+            tc_split(al, a1, a2);
+            resid[i] = al - (double)__half2float(a1) - (double)__half2float(a2) * (double)kTcLoInv;
+            opA_out[tc_index(i, kseg - 1, kc)] = a1;
+            opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
+        } else {
+            __half a1, a2, a3;
+            // the residual is applied to the finished sum in float64 and is not subject to the accumulator's truncation
+            resid[i] = tc_split3(fmax(al * (1.0 + kTcTruncComp), (double)kTcPad), a1, a2, a3) / (1.0 + kTcTruncComp);
+            opA_out[tc_index(i, kseg - 1, kc)] = a1;
+            opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
+            opA_out[tc_index(i, 3 * kseg - 1, kc)] = a3;
+        }
     }
-    if (i < n_in) {
-        const double be = fmax(off_in[i], (double)kTcPad);
-        __half b1, b2;
-        tc_split(be, b1, b2);
-        opB_in[tc_index(i, kseg - 2, kc)] = b1;
-        opB_in[tc_index(i, 3 * kseg - 2, kc)] = b2;
+    if (i < n_in) tc_store_in_offset(opB_in, i, off_in[i], kseg, nseg);
+}
+
+// max |x_ik|, max |x_i|^2 over one side into the solve's TcGeo (non-negative doubles order like their bit patterns, so
+// the atomic maximum is exact and order independent)
+__global__ void k_tc_geo(const double *__restrict__ x, int n, int d, TcGeo *geo, int side) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double ma = 0.0, n2 = 0.0;
+    if (i < n) {
+        for (int k = 0; k < d; ++k) {
+            const double v = x[(long long)i * d + k];
+            ma = fmax(ma, fabs(v));
+            n2 = fma(v, v, n2);
+        }
+    }
+    ma = warp_max(ma);
+    n2 = warp_max(n2);
+    if ((threadIdx.x & 31) == 0) {
+        atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&geo->max_abs), ma);
+        atomic_max_nonneg(reinterpret_cast<unsigned long long *>(side == 0 ? &geo->max_n2x : &geo->max_n2y), n2);
     }
 }
 
@@ -329,39 +409,75 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// ---- shared-memory barriers by 32-bit shared address: the loops below keep every address in a register instead of
+// re-deriving it from a generic pointer each time (profiles/r2a: ~100 of the 282 instructions of the epilogue loop
+// were address arithmetic, clock reads of the disabled profiler and barrier bookkeeping) ------------------------------
+__device__ __forceinline__ void tcb_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tcb_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcb_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tcb_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void tcb_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tcb_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // One pass = (out blocks) x (in tiles) work units of 256 x 128 entries, dealt to the CTAs of a one-wave
 // grid in contiguous ranges (block-major), "stream-K" style: every SM gets the same number of units whatever
 // the shape, and the per-CTA fixed cost (TMEM allocation, barrier setup, pipeline fill) is paid once.  A CTA's
-// range may cross out-block boundaries; the A blocks are double buffered so the switch costs nothing.  Each
-// (out block, CTA) pair writes its partial row sums into its own slot; the last CTA to arrive at an out block
-// adds the slots in slot order and applies the update, so the result does not depend on timing.
+// range may cross out-block boundaries; the A blocks are double buffered (3-segment operands) so the switch costs
+// nothing.  Each (out block, CTA) pair writes its partial row sums into its own slot; the last CTA to arrive at an
+// out block adds the slots in slot order and applies the update, so the result does not depend on timing.
 //
 // modes as in k_online_pass: 0 half-step, 1 row sums for the gap, 2 coupling row sums, 3 S0 partials,
 // 4 partial sums only (row-sharded solves).  EW = epilogue warps per row block (4: thread = row x 128 columns,
-// 8: thread = row x 64 columns).
-template <bool COLPASS, int KSEG, int EW>
+// 8: thread = row x 64 columns).  NSEG = K segments per operand row (3, or 6 in precise mode: twice the MMAs per
+// tile, A single buffered).  PROF: measurement build with cycle counters and the dbg switches of TcArgs.
+template <bool COLPASS, int KSEG, int EW, int NSEG, bool PROF>
 __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     k_online_tc(TcArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
     constexpr int RB = kTcRowBlocks, NT = kTcN;
     constexpr int kEpiThreads = RB * EW * 32;
     constexpr int NCH = 4 / (EW / 4);  // 32-column chunks per tile and warp
     constexpr int kseg = KSEG;
-    constexpr uint32_t row_bytes = (uint32_t)kseg * 6u;  // 3 * kseg halves
+    constexpr int NABUF = NSEG == 3 ? 2 : 1;
+    constexpr uint32_t row_bytes = (uint32_t)kseg * NSEG * 2u;
     constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
     extern __shared__ __align__(128) unsigned char tc_smem[];
     __shared__ int is_last;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int S = A.n_stages;
-    unsigned char *sA = tc_smem;                      // [2 buffers][RB blocks]
-    unsigned char *sB = sA + 2 * RB * a_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sB + (size_t)S * b_bytes);
-    uint64_t *empty = full + kTcMaxStages;
-    uint64_t *acc_full = empty + kTcMaxStages;  // [buffer][row block]
-    uint64_t *acc_empty = acc_full + 2 * RB;
-    uint64_t *a_full = acc_empty + 2 * RB;      // [A buffer]
-    uint64_t *a_empty = a_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 2);
-    double *red = reinterpret_cast<double *>(full) + 32;  // [RB * 128]: second column half of every row (EW == 8)
+    // shared memory map (32-bit shared addresses): barriers + reduction scratch (kTcTail bytes, at fixed offsets so
+    // that a barrier address is the base plus a constant) | A blocks | B ring
+    const uint32_t smem0 = smem_u32(tc_smem);
+    const uint32_t bars = smem0;
+    const uint32_t sA = smem0 + kTcTail, sB = sA + NABUF * RB * a_bytes;
+    const uint32_t b_full = bars, b_empty = bars + 8 * kTcMaxStages;
+    const uint32_t b_accf = b_empty + 8 * kTcMaxStages;  // [buffer][row block]
+    const uint32_t b_acce = b_accf + 8 * 2 * RB;
+    const uint32_t b_af = b_acce + 8 * 2 * RB, b_ae = b_af + 16;
+    unsigned char *bars_p = tc_smem + (bars - smem0);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars_p + 8 * (2 * kTcMaxStages + 4 * RB + 4));
+    double *red = reinterpret_cast<double *>(bars_p) + 32;  // [RB * 128]: second column half of every row (EW == 8)
 
     const int nt = A.in_ntiles;
     const long long T = (long long)A.n_blocks * nt;
@@ -371,16 +487,16 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], RB);  // one commit per MMA warp
+            tcb_init(b_full + 8 * s, 1);
+            tcb_init(b_empty + 8 * s, RB);  // one commit per MMA warp
         }
         for (int b = 0; b < 2 * RB; ++b) {
-            mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], EW);  // the warps that drain it
+            tcb_init(b_accf + 8 * b, 1);
+            tcb_init(b_acce + 8 * b, EW);  // the warps that drain it
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&a_full[b], 1);
-            mbar_init(&a_empty[b], RB);
+            tcb_init(b_af + 8 * b, 1);
+            tcb_init(b_ae + 8 * b, RB);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -420,17 +536,19 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             int s = 0, seg = 0, b = b_first, t = t_first;
             uint32_t empty_par = 1;
             for (long long g = g0; g < g1; ++seg, ++b, t = 0) {
-                const int abuf = seg & 1;
-                mbar_wait_bounded(&a_empty[abuf], (uint32_t)(((seg >> 1) & 1) ^ 1));
-                mbar_expect_tx(&a_full[abuf], RB * a_bytes);
+                const int abuf = NABUF == 2 ? (seg & 1) : 0;
+                const uint32_t a_par = (uint32_t)(NABUF == 2 ? (seg >> 1) & 1 : seg & 1);
+                tcb_wait(b_ae + 8 * abuf, a_par ^ 1u);
+                tcb_expect_tx(b_af + 8 * abuf, RB * a_bytes);
                 const unsigned char *blockA = srcA + (size_t)(A.out_blk0 + b) * (RB * a_bytes);
                 for (int rb = 0; rb < RB; ++rb)
-                    bulk_g2s(sA + (abuf * RB + rb) * a_bytes, blockA + (size_t)rb * a_bytes, a_bytes, &a_full[abuf]);
+                    tcb_bulk_g2s(sA + (abuf * RB + rb) * a_bytes, blockA + (size_t)rb * a_bytes, a_bytes, b_af + 8 * abuf);
                 const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
                 for (int k = 0; k < n_in_seg; ++k) {
-                    mbar_wait_bounded(&empty[s], empty_par);
-                    mbar_expect_tx(&full[s], b_bytes);
-                    bulk_g2s(sB + (size_t)s * b_bytes, srcB + (size_t)(A.in_tile0 + t + k) * b_bytes, b_bytes, &full[s]);
+                    tcb_wait(b_empty + 8 * s, empty_par);
+                    tcb_expect_tx(b_full + 8 * s, b_bytes);
+                    tcb_bulk_g2s(sB + (uint32_t)s * b_bytes, srcB + (size_t)(A.in_tile0 + t + k) * b_bytes, b_bytes,
+                                 b_full + 8 * s);
                     if (++s == S) {
                         s = 0;
                         empty_par ^= 1u;
@@ -447,33 +565,37 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
         // control flow and descriptors), one elected lane issues.  Measured: the issuing warp, not the tensor pipe, is
         // what can bound this kernel -- an MMA costs ~48 clocks back to back, but a barrier wait ~150-250 and a commit
         // ~200, and with per-lane descriptor arithmetic ~100 per instruction -- hence one issuing warp per row block,
-        // so that each spends one accumulator wait, six MMAs and two commits per 256 x 128 unit =====
+        // so that each spends one accumulator wait, its MMAs and two commits per 256 x 128 unit =====
         // instruction descriptor: D fp32 (bit 4), A/B fp16 (format 0), both K-major, N, M
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
-        const bool skip_mma = (A.dbg & 1) != 0;
-        constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * 48u;  // 3*kseg/8 chunks of 16 B per row, 128 B per 8 rows
-        constexpr int ksteps = 3 * kseg / 16;                       // K = 16 halves = two chunks per instruction
+        const bool skip_mma = PROF && (A.dbg & 1) != 0;
+        constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * NSEG * 16u;  // NSEG*kseg/8 chunks of 16 B per row, 128 B per 8 rows
+        constexpr int ksteps = NSEG * kseg / 16;                           // K = 16 halves = two chunks per instruction
         const int rb = wid - 1;
-        const uint64_t descA0 = umma_desc(smem_u32(sA), lbo, sbo);
-        const uint64_t descB0 = umma_desc(smem_u32(sB), lbo, sbo);
+        const uint64_t descA0 = umma_desc(sA, lbo, sbo);
+        const uint64_t descB0 = umma_desc(sB, lbo, sbo);
         int s = 0, seg = 0, t = t_first;
         uint32_t full_par = 0, u = 0;
-        const bool mprof = (A.dbg & 8) != 0;
-        long long m_t0 = clock64(), m_full = 0, m_acc = 0, m_issue = 0, m_x = 0;
-#define TC_M0() if (mprof) m_x = clock64()
-#define TC_M1(dst) if (mprof) dst += clock64() - m_x
+        const bool mprof = PROF && (A.dbg & 8) != 0;
+        long long m_t0 = PROF ? clock64() : 0, m_full = 0, m_acc = 0, m_issue = 0, m_x = 0;
+#define TC_M0() if (PROF && mprof) m_x = clock64()
+#define TC_M1(dst) if (PROF && mprof) dst += clock64() - m_x
         for (long long g = g0; g < g1; ++seg, t = 0) {
-            const int abuf = seg & 1;
-            mbar_wait_warp(&a_full[abuf], (uint32_t)((seg >> 1) & 1));
+            const int abuf = NABUF == 2 ? (seg & 1) : 0;
+            const uint32_t a_par = (uint32_t)(NABUF == 2 ? (seg >> 1) & 1 : seg & 1);
+            tcb_wait(b_af + 8 * abuf, a_par);
+            __syncwarp();
             const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
             const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
             for (int k = 0; k < n_in_seg; ++k, ++u) {
                 const uint32_t buf = u & 1u, par = (u >> 1) & 1u;
                 TC_M0();
-                mbar_wait_warp(&acc_empty[buf * RB + rb], par ^ 1u);
+                tcb_wait(b_acce + 8 * (buf * RB + rb), par ^ 1u);
+                __syncwarp();
                 TC_M1(m_acc);
                 TC_M0();
-                mbar_wait_warp(&full[s], full_par);
+                tcb_wait(b_full + 8 * s, full_par);
+                __syncwarp();
                 TC_M1(m_full);
                 tc_fence_after();
                 TC_M0();
@@ -485,9 +607,9 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                         for (int j = 0; j < ksteps; ++j)
                             umma_f16(d_tmem, descA + (uint64_t)(j * 16), descB + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
                     }
-                    umma_commit(&acc_full[buf * RB + rb]);
-                    umma_commit(&empty[s]);                              // the stage is free once both warps' MMAs have read it
-                    if (k == n_in_seg - 1) umma_commit(&a_empty[abuf]);  // and so are the A blocks of this segment
+                    tcb_commit(b_accf + 8 * (buf * RB + rb));
+                    tcb_commit(b_empty + 8 * s);                              // the stage is free once both warps' MMAs have read it
+                    if (k == n_in_seg - 1) tcb_commit(b_ae + 8 * abuf);       // and so are the A blocks of this segment
                 }
                 __syncwarp();
                 TC_M1(m_issue);
@@ -498,7 +620,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             }
             g += n_in_seg;
         }
-        if (mprof && lane == 0 && rb == 0) {
+        if (PROF && mprof && lane == 0 && rb == 0) {
             long long *dst = A.prof + ((long long)gridDim.x * 16 + blockIdx.x) * 8;
             dst[0] = clock64() - m_t0, dst[1] = m_full, dst[2] = m_acc, dst[3] = m_issue, dst[4] = (long long)u;
         }
@@ -509,19 +631,23 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
         const int ew = wid - kTcEpiWarp0;
         const int rb = ew / EW, within = ew % EW;
         const int q = within & 3, h = within >> 2;
-        const uint32_t lane_col = ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32));
-        const bool skip_exp = (A.dbg & 2) != 0;
-        const bool prof = (A.dbg & 8) != 0;
-        long long c_acc = 0, c_ld = 0, c_t0 = clock64(), c_x = 0, c_pro = 0, c_fin = 0;
-#define TC_T0() if (prof) c_x = clock64()
-#define TC_T1(dst) if (prof) dst += clock64() - c_x
+        const bool skip_exp = PROF && (A.dbg & 2) != 0;
+        const bool prof = PROF && (A.dbg & 8) != 0;
+        long long c_acc = 0, c_ld = 0, c_t0 = PROF ? clock64() : 0, c_x = 0, c_pro = 0, c_fin = 0;
+#define TC_T0() if (PROF && prof) c_x = clock64()
+#define TC_T1(dst) if (PROF && prof) dst += clock64() - c_x
         uint32_t va[32], vb[32];
         const uint32_t n_units = (uint32_t)(g1 - g0);
+        // loop-carried addresses: accumulator buffer `cur` of this row block (TMEM columns and the two barriers);
+        // the other buffer is reached by XOR with the precomputed differences
+        const uint32_t t_buf0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32));
+        const uint32_t accf0 = b_accf + 8 * rb, acce0 = b_acce + 8 * rb;
+        constexpr uint32_t kBufBar = 8 * RB;  // barrier distance between buffer 0 and buffer 1
         if (!skip_exp) {
-            mbar_wait_bounded(&acc_full[rb], 0);
+            tcb_wait(accf0, 0);
             tc_fence_after();
-            WOTB_TMEM_LD32(va, tmem_base + lane_col);
-            if (prof) c_pro = clock64() - c_t0;
+            WOTB_TMEM_LD32(va, t_buf0);
+            if (PROF && prof) c_pro = clock64() - c_t0;
         }
         int seg = 0, b = b_first, t = t_first;
         uint32_t u = 0;
@@ -529,52 +655,52 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
             double acc = 0.0;
             for (int k0 = 0; k0 < n_in_seg; k0 += 8) {
-                // fp32 across 8 tiles (<= 1024 positive terms), then float64: the FP64 pipe stays out of the tile loop
-                float facc = 0.f;
-                const int k1 = min(k0 + 8, n_in_seg);
-                for (int k = k0; k < k1; ++k, ++u) {
-                    const uint32_t buf = u & 1u;
-                    const uint32_t taddr = tmem_base + lane_col + buf * kTcAccCols;
-                    if (skip_exp) {
-                        mbar_wait_bounded(&acc_full[buf * RB + rb], (u >> 1) & 1u);
+            // fp32 across 8 tiles (<= 1024 positive terms), then float64: the FP64 pipe stays out of the tile loop
+            float facc = 0.f;
+            const int k1 = min(k0 + 8, n_in_seg);
+            for (int k = k0; k < k1; ++k, ++u) {
+                const uint32_t buf = u & 1u;
+                const uint32_t taddr = t_buf0 + buf * kTcAccCols;
+                if (PROF && skip_exp) {
+                    tcb_wait(accf0 + buf * kBufBar, (u >> 1) & 1u);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tcb_arrive(acce0 + buf * kBufBar);
+                    continue;
+                }
+                float tile_sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < NCH; c += 2) {
+                    TC_T0();
+                    WOTB_TMEM_WAIT32(va);  // chunk c (issued one step earlier)
+                    TC_T1(c_ld);
+                    WOTB_TMEM_LD32(vb, taddr + (c + 1) * 32);
+                    tile_sum += tc_exp2_sum32(va);
+                    TC_T0();
+                    WOTB_TMEM_WAIT32(vb);
+                    TC_T1(c_ld);
+                    if (c + 2 < NCH) {
+                        WOTB_TMEM_LD32(va, taddr + (c + 2) * 32);
+                    } else {
+                        // every column of this accumulator is in registers: hand it back to the MMA warp, and
+                        // fetch the first columns of the next unit while the last 32 of this one are evaluated
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[buf * RB + rb]);
-                        continue;
-                    }
-                    float tile_sum = 0.f;
-#pragma unroll
-                    for (int c = 0; c < NCH; c += 2) {
-                        TC_T0();
-                        WOTB_TMEM_WAIT32(va);  // chunk c (issued one step earlier)
-                        TC_T1(c_ld);
-                        WOTB_TMEM_LD32(vb, taddr + (c + 1) * 32);
-                        tile_sum += tc_exp2_sum32(va);
-                        TC_T0();
-                        WOTB_TMEM_WAIT32(vb);
-                        TC_T1(c_ld);
-                        if (c + 2 < NCH) {
-                            WOTB_TMEM_LD32(va, taddr + (c + 2) * 32);
-                        } else {
-                            // every column of this accumulator is in registers: hand it back to the MMA warp, and
-                            // fetch the first columns of the next unit while the last 32 of this one are evaluated
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&acc_empty[buf * RB + rb]);
-                            if (u + 1 < n_units) {
-                                const uint32_t nb = (u + 1) & 1u;
-                                TC_T0();
-                                mbar_wait_bounded(&acc_full[nb * RB + rb], ((u + 1) >> 1) & 1u);
-                                TC_T1(c_acc);
-                                tc_fence_after();
-                                WOTB_TMEM_LD32(va, tmem_base + lane_col + nb * kTcAccCols);
-                            }
+                        if (lane == 0) tcb_arrive(acce0 + buf * kBufBar);
+                        if (u + 1 < n_units) {
+                            const uint32_t nb = buf ^ 1u;
+                            TC_T0();
+                            tcb_wait(accf0 + nb * kBufBar, ((u + 1) >> 1) & 1u);
+                            TC_T1(c_acc);
+                            tc_fence_after();
+                            WOTB_TMEM_LD32(va, t_buf0 + nb * kTcAccCols);
                         }
-                        tile_sum += tc_exp2_sum32(vb);
                     }
-                    facc += tile_sum;
+                    tile_sum += tc_exp2_sum32(vb);
                 }
-                acc += (double)facc;
+                facc += tile_sum;
+            }
+            acc += (double)facc;
             }
             g += n_in_seg;
             // ---- this CTA's share of out block b is complete: publish it, and finish the block if it is the last ----
@@ -627,7 +753,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             }
             TC_T1(c_fin);
         }
-        if (prof && lane == 0) {
+        if (PROF && prof && lane == 0) {
             long long *dst = A.prof + ((long long)blockIdx.x * (RB * EW) + ew) * 8;
             dst[0] = clock64() - c_t0, dst[1] = c_acc, dst[2] = c_ld, dst[3] = (long long)n_units;
             dst[4] = c_pro, dst[5] = c_fin;
@@ -648,17 +774,22 @@ inline int tc_kseg(int d) { return (int)round_up(d + 2, 16); }
 inline bool tc_supported(int d) { return tc_kseg(d) <= kTcMaxKseg; }
 
 struct TcPlan {
-    int kseg = 0, n_stages = 0, ew = 4;
+    int kseg = 0, n_stages = 0, ew = 4, nseg = 3;
+    bool prof = false;  // measurement build (cycle counters, dbg switches); kseg 32 only
     size_t smem = 0;
     int threads() const { return 128 + kTcRowBlocks * ew * 32; }
+    size_t row_bytes() const { return (size_t)kseg * nseg * 2; }
 };
 
-inline TcPlan tc_plan(int d, int ew = 4) {
+// nseg 3: the default fp16 hi/lo operands; nseg 6: precise mode (always 16 epilogue warps)
+inline TcPlan tc_plan(int d, int ew = 4, int nseg = 3, bool prof = false) {
     TcPlan p;
     p.kseg = tc_kseg(d);
-    p.ew = ew;
-    const size_t row_bytes = (size_t)p.kseg * 6;
-    const size_t a = 2 * (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes;  // A double buffered
+    p.nseg = nseg;
+    p.ew = nseg == 6 ? 8 : ew;
+    p.prof = prof && p.kseg == 32;
+    const size_t row_bytes = p.row_bytes();
+    const size_t a = (nseg == 3 ? 2 : 1) * (size_t)kTcOut * row_bytes, b = (size_t)kTcN * row_bytes;  // A double buffered (3 segments)
     int s = (int)((kTcSmemLimit - a - kTcTail) / b);
     if (s > kTcMaxStages) s = kTcMaxStages;
     p.n_stages = s;
@@ -674,26 +805,23 @@ inline int tc_grid(int sm_count, int n_blocks, int in_tiles, int *max_slots) {
     return G;
 }
 
-template <int KSEG, int EW>
-inline int tc_configure_one(int bytes) {
-    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<false, KSEG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    WOTB_CUDA(cudaFuncSetAttribute(k_online_tc<true, KSEG, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return WOTB_OK;
-}
+// the instantiations that exist: (kseg, epilogue warps per row block, segments, profiling build)
+#define WOTB_TC_VARIANTS(X) \
+    X(16, 4, 3, false) X(32, 4, 3, false) X(48, 4, 3, false) X(16, 8, 3, false) X(32, 8, 3, false) X(48, 8, 3, false) \
+    X(16, 8, 6, false) X(32, 8, 6, false) X(48, 8, 6, false) X(32, 4, 3, true) X(32, 8, 3, true) X(32, 8, 6, true)
 
 inline int tc_configure(const TcPlan &plan) {
-    static size_t configured[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    const int k = plan.kseg / 16 - 1, e = plan.ew == 8;
-    if (configured[k][e] < plan.smem) {
-        const int bytes = (int)plan.smem;
-        if (plan.kseg == 16 && !e) WOTB_TRY((tc_configure_one<16, 4>(bytes)));
-        if (plan.kseg == 32 && !e) WOTB_TRY((tc_configure_one<32, 4>(bytes)));
-        if (plan.kseg == 48 && !e) WOTB_TRY((tc_configure_one<48, 4>(bytes)));
-        if (plan.kseg == 16 && e) WOTB_TRY((tc_configure_one<16, 8>(bytes)));
-        if (plan.kseg == 32 && e) WOTB_TRY((tc_configure_one<32, 8>(bytes)));
-        if (plan.kseg == 48 && e) WOTB_TRY((tc_configure_one<48, 8>(bytes)));
-        configured[k][e] = plan.smem;
+    cudaError_t e = cudaErrorInvalidValue;
+    const int bytes = (int)plan.smem;
+#define WOTB_TC_CFG(K, E, N, P)                                                                                          \
+    if (plan.kseg == K && plan.ew == E && plan.nseg == N && plan.prof == P) {                                            \
+        e = cudaFuncSetAttribute(k_online_tc<false, K, E, N, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);    \
+        if (e == cudaSuccess)                                                                                            \
+            e = cudaFuncSetAttribute(k_online_tc<true, K, E, N, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     }
+    WOTB_TC_VARIANTS(WOTB_TC_CFG)
+#undef WOTB_TC_CFG
+    WOTB_CUDA(e);
     return WOTB_OK;
 }
 
@@ -716,7 +844,7 @@ inline bool tc_use_pdl() {
     return use == 1;
 }
 
-template <bool COLPASS, int K, int E>
+template <bool COLPASS, int K, int E, int N, bool P>
 inline void tc_launch_one(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
                           int mode, double *rowsum_out) {
     cudaLaunchConfig_t cfg;
@@ -726,23 +854,18 @@ inline void tc_launch_one(const TcPlan &plan, int grid, cudaStream_t st, const T
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr, cfg.numAttrs = tc_use_pdl() ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, k_online_tc<COLPASS, K, E>, A, V, ctrl, mode, rowsum_out);
+    cudaLaunchKernelEx(&cfg, k_online_tc<COLPASS, K, E, N, P>, A, V, ctrl, mode, rowsum_out);
 }
 
 template <bool COLPASS>
 inline void tc_launch(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl,
                       int mode, double *rowsum_out) {
-#define WOTB_TC_CASE(K, E)                                                                   \
-    if (plan.kseg == K && plan.ew == E) {                                                    \
-        tc_launch_one<COLPASS, K, E>(plan, grid, st, A, V, ctrl, mode, rowsum_out);          \
+#define WOTB_TC_CASE(K, E, N, P)                                                             \
+    if (plan.kseg == K && plan.ew == E && plan.nseg == N && plan.prof == P) {                \
+        tc_launch_one<COLPASS, K, E, N, P>(plan, grid, st, A, V, ctrl, mode, rowsum_out);    \
         return;                                                                              \
     }
-    WOTB_TC_CASE(16, 4)
-    WOTB_TC_CASE(32, 4)
-    WOTB_TC_CASE(48, 4)
-    WOTB_TC_CASE(16, 8)
-    WOTB_TC_CASE(32, 8)
-    WOTB_TC_CASE(48, 8)
+    WOTB_TC_VARIANTS(WOTB_TC_CASE)
 #undef WOTB_TC_CASE
 }
 
@@ -763,8 +886,8 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     WOTB_REQUIRE(n_out >= 1 && n_in >= 1 && d >= 1 && reps >= 0, "bad sizes");
     const int dbg = impl >> 4;
     impl &= 15;
-    WOTB_REQUIRE(impl == 0 || ((impl == 1 || impl == 2) && tc_supported(d)),
-                 "impl: 0 SIMT FP32, 1 tcgen05 with 8 epilogue warps, 2 tcgen05 with 16 (d <= 46)");
+    WOTB_REQUIRE(impl == 0 || ((impl >= 1 && impl <= 3) && tc_supported(d)),
+                 "impl: 0 SIMT FP32, 1 tcgen05 with 8 epilogue warps, 2 tcgen05 with 16, 3 tcgen05 precise mode (d <= 46)");
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     wotb_params prm;
@@ -789,28 +912,35 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
     float ms = 0.f;
     int grid_used = 0;
     if (impl >= 1) {
-        const TcPlan plan = tc_plan(d, impl == 2 ? 8 : 4);
+        const TcPlan plan = tc_plan(d, impl == 1 ? 4 : 8, impl == 3 ? 6 : 3, dbg != 0);
+        WOTB_REQUIRE(dbg == 0 || plan.prof, "the measurement switches exist for kseg = 32 (15 <= d <= 30) only");
         WOTB_TRY(tc_configure(plan));
         const int64_t po = round_up(n_out, kTcOut), pi = round_up(n_in, kTcOut);
-        const size_t row_bytes = (size_t)plan.kseg * 6;
+        const size_t row_bytes = plan.row_bytes();
         const int out_blocks = (int)cdiv(n_out, kTcOut), in_tiles = (int)cdiv(n_in, kTcN);
         int max_slots = 0;
         const int grid = tc_grid(ctx->sm_count, out_blocks, in_tiles, &max_slots);
         grid_used = grid;
         const size_t o_ao = take(po * row_bytes), o_bo = take(po * row_bytes), o_ai = take(pi * row_bytes),
                      o_bi = take(pi * row_bytes), o_res = take(po * 8), o_part = take((size_t)max_slots * po * 8),
-                     o_cnt = take((size_t)out_blocks * 4 + 64);
+                     o_cnt = take((size_t)out_blocks * 4 + 64), o_geo = take(sizeof(TcGeo));
         WOTB_TRY(ctx->onl.reserve(off));
         char *ob = ctx->onl.as<char>();
         __half *Ao = (__half *)(ob + o_ao), *Bo = (__half *)(ob + o_bo), *Ai = (__half *)(ob + o_ai), *Bi = (__half *)(ob + o_bi);
         double *resid = (double *)(ob + o_res), *part = (double *)(ob + o_part);
         unsigned int *cnt = (unsigned int *)(ob + o_cnt);
+        TcGeo *geo = (TcGeo *)(ob + o_geo);
         WOTB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)out_blocks * 4, st));
+        WOTB_CUDA(cudaMemsetAsync(geo, 0, sizeof(TcGeo), st));
+        k_tc_geo<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(x_out, (int)n_out, d, geo, 0);
+        k_tc_geo<<<(unsigned)cdiv(n_in, 256), 256, 0, st>>>(x_in, (int)n_in, d, geo, 1);
         const int cpr = plan.kseg / 8;
-        k_tc_pack<<<(unsigned)cdiv(po * cpr, 256), 256, 0, st>>>(x_out, (int)n_out, d, po, plan.kseg, Ao, Bo, nullptr, scale);
-        k_tc_pack<<<(unsigned)cdiv(pi * cpr, 256), 256, 0, st>>>(x_in, (int)n_in, d, pi, plan.kseg, Ai, Bi, nullptr, scale);
+        k_tc_pack<<<(unsigned)cdiv(po * cpr, 256), 256, 0, st>>>(x_out, (int)n_out, d, po, plan.kseg, plan.nseg, Ao, Bo, nullptr,
+                                                                 scale, geo);
+        k_tc_pack<<<(unsigned)cdiv(pi * cpr, 256), 256, 0, st>>>(x_in, (int)n_in, d, pi, plan.kseg, plan.nseg, Ai, Bi, nullptr,
+                                                                 scale, geo);
         k_tc_slots<<<(unsigned)cdiv(n_out > n_in ? n_out : n_in, 256), 256, 0, st>>>(off_out, (int)n_out, Ao, resid, off_in,
-                                                                                     (int)n_in, Bi, plan.kseg, nullptr, 0);
+                                                                                     (int)n_in, Bi, plan.kseg, plan.nseg, nullptr, 0);
         TcArgs A;
         A.opA = Ao, A.opB = Bi, A.resid = resid, A.out_n = (int)n_out, A.out_ld = po;
         A.n_blocks = out_blocks, A.out_blk0 = 0, A.in_tile0 = 0, A.in_ntiles = in_tiles;

@@ -821,6 +821,7 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.n_pad_i = V.n_pad_j = 0;
     V.tcXB = V.tcYB = nullptr;
     V.tc_kseg = 0;
+    V.tc_nseg = 3;
     WOTB_CUDA(cudaMemsetAsync(V.tile_counters, 0, (size_t)n_col_tiles * 4 + 64, ctx->stream));
     WOTB_CUDA(cudaMemsetAsync(V.sumK0_part, 0, (size_t)n_k0_part * 8 + 64, ctx->stream));
     *out = V;

@@ -85,4 +85,5 @@ struct SolveVecs {
     // ---- tcgen05 online kernel only: the B-role operand rows whose offset slots follow Pd / Qd (online_tc.cuh) ----
     __half *tcXB, *tcYB;
     int tc_kseg;
+    int tc_nseg;  // 3: fp16 hi/lo split (default); 6: precise mode, grid-aligned leading limb + two more limbs
 };

@@ -17,6 +17,35 @@ def check_file_extension(name, output_format):
     return name
 
 
+def check_output_format(output_format):
+    """Raise for a format this installation cannot write BEFORE any transport map is computed."""
+    if output_format not in ("h5ad", "loom", "txt", "npz"):
+        raise ValueError("Unknown file format")
+    if output_format == "loom" and not HAVE_ANNDATA:
+        raise ImportError("writing .loom needs the anndata and loompy packages; use 'h5ad', 'txt' or 'npz'")
+
+
+class TmapWriter:
+    """write_dataset behind the caller's back: at most `depth` maps wait for the disk while the next ones are being
+    solved (each waiting map pins its 0.2-3 GB block, hence the bound).  close() waits and re-raises a failed write."""
+
+    def __init__(self, output_format, depth=2):
+        from . import h5ad
+        self.output_format = output_format
+        self._async = h5ad.AsyncWriter(depth=depth)
+
+    def write(self, ds, path):
+        fmt = self.output_format
+        self._async.submit(lambda: write_dataset(ds, path, output_format=fmt))
+
+    def close(self, quiet=False):
+        try:
+            self._async.close()
+        except BaseException:
+            if not quiet:
+                raise
+
+
 def write_dataset(ds, path, output_format="txt"):
     """io.py:439-452, plus an 'npz' format usable without anndata/h5py."""
     path = check_file_extension(str(path), output_format)
@@ -40,10 +69,15 @@ def read_dataset(path):
     path = str(path)
     low = path.lower()
     if low.endswith(".h5ad"):
-        if not HAVE_ANNDATA:
-            raise ImportError("reading .h5ad needs the anndata package")
-        import anndata
-        return anndata.read_h5ad(path)
+        if HAVE_ANNDATA:
+            import anndata
+            return anndata.read_h5ad(path)
+        # the built-in reader handles the dense, uncompressed classic-format layout (what this package writes and
+        # what anndata writes by default for a dense float matrix with float obs columns)
+        from . import h5ad
+        d = h5ad.read_h5ad(path)
+        obs = pd.DataFrame({k: v for k, v in d["obs"].items()}, index=pd.Index(d["obs_index"].astype(str)))
+        return AnnData(d["X"], obs, pd.DataFrame(index=pd.Index(d["var_index"].astype(str))))
     if low.endswith(".npz"):
         z = np.load(path, allow_pickle=False)
         obs = pd.DataFrame(index=pd.Index(z["obs_index"].astype(str)))

@@ -33,26 +33,31 @@ def last_solve_info():
 
 def resolve_kernel(kernel, n_i, n_j, d, epsilon=0.05):
     """'auto' -> 'online' or 'stored'.  The online kernel (K recomputed tile by tile on tcgen05 + MUFU, nothing of
-    size I x J in memory) is the faster one on B200.  Its exponent is accumulated in fp32 (TMEM), so its error
-    grows like 1/epsilon: ~1e-5 at the default 0.05, ~5e-5 at 0.01, where couplings still hold 1e-4 but slowly
-    converging settings (large lambdas) end a few batches away from the reference
-    (tests/test_gpu_parity.py::test_sweep_settings_vs_oracle).  The stored kernel (fp32 K built from a float64
-    exponent, error ~1e-6 whatever epsilon) is therefore kept for final epsilon < 0.02 and for d > 46."""
+    size I x J in memory) is the faster one on B200 and is used whenever the coordinates fit its K budget (d <= 46).
+    Below a final epsilon of 0.02 the library switches its operands to the precise 6-segment form (leading limb on a
+    fixed-point grid, exact accumulation of the large cancelling terms: exponent error ~1e-6 whatever epsilon, about
+    twice the tensor-core work), so that slowly converging settings reproduce the reference's batch counts
+    (tests/test_gpu_parity.py::test_sweep_settings_vs_oracle)."""
     if kernel != "auto":
         return kernel
-    return "online" if d <= 46 and float(epsilon) >= 0.02 else "stored"
+    return "online" if d <= 46 else "stored"
 
 
 def _kernel_id(kernel):
-    """(wotb_kernel, force_simt).  'online' uses the tcgen05 pass kernel when d <= 46 and the SIMT FP32 kernel
-    otherwise; 'online_simt' forces the latter."""
+    """(wotb_kernel, force_simt, precise).  'online' uses the tcgen05 pass kernel when d <= 46 (precise operands
+    below final epsilon 0.02) and the SIMT FP32 kernel otherwise; 'online_simt' forces the latter; 'online_fast' /
+    'online_precise' pin the operand form of the tcgen05 pass."""
     if kernel in (None, "stored", _lib.KERNEL_STORED):
-        return _lib.KERNEL_STORED, False
+        return _lib.KERNEL_STORED, False, None
     if kernel in ("online", _lib.KERNEL_ONLINE):
-        return _lib.KERNEL_ONLINE, False
+        return _lib.KERNEL_ONLINE, False, None
     if kernel == "online_simt":
-        return _lib.KERNEL_ONLINE, True
-    raise ValueError("kernel must be 'stored', 'online' or 'online_simt'")
+        return _lib.KERNEL_ONLINE, True, None
+    if kernel == "online_fast":
+        return _lib.KERNEL_ONLINE, False, False
+    if kernel == "online_precise":
+        return _lib.KERNEL_ONLINE, False, True
+    raise ValueError("kernel must be 'stored', 'online', 'online_fast', 'online_precise' or 'online_simt'")
 
 
 def _out_array(shape, out, out_dtype, pinned):
@@ -122,8 +127,8 @@ def solve_coords(x0, x1, G, solver_id, scale=None, growth_iters=1, kernel="auto"
     if solver_id == _lib.SOLVER_DUALITY_GAP:
         eps_final *= float(params.get("epsilon0", 1.0))
     kernel = resolve_kernel(kernel, n_i, n_j, d, eps_final)
-    kernel_id, simt = _kernel_id(kernel)
-    prm = _lib.make_params(solver=solver_id, kernel=kernel_id, online_simt=simt, **params)
+    kernel_id, simt, precise = _kernel_id(kernel)
+    prm = _lib.make_params(solver=solver_id, kernel=kernel_id, online_simt=simt, online_precise=precise, **params)
     ctx = ctx or _lib.context(device)
     tmap = _out_array((n_i, n_j), out, out_dtype, pinned) if want_tmap else None
     learned = np.empty((growth_iters + 1, n_i))

@@ -176,11 +176,16 @@ class OTModel:
                 continue
             todo.append((day_pair, cost_matrix, output_file))
 
+        _io.check_output_format(output_file_format)      # fail before any GPU work, not after the first solve
+        # files are written behind the solves: the map sits in a page-locked block that stays alive until its file
+        # is complete, the worker goes on to its next day-pair (wot_b200/h5ad.py)
+        writer = _io.TmapWriter(output_file_format)
+
         def one(day_pair, cost_matrix, output_file):
             tmap = self.compute_transport_map(*day_pair, cost_matrix=cost_matrix)
             if tmap is None:
                 return None
-            _io.write_dataset(tmap, output_file, output_format=output_file_format)
+            writer.write(tmap, output_file)
             return tmap.obs if keep_growth else None
 
         ours = self.solver in (_ot.optimal_transport_duality_gap, _ot.transport_stablev2)
@@ -192,10 +197,15 @@ class OTModel:
             from ..pipeline import Pipeline
             counts = self.matrix.obs[self.day_field].value_counts()
             costs = [float(counts.get(job[0][0], 0)) * float(counts.get(job[0][1], 0)) for job in todo]
-            with Pipeline(streams=self.streams + 1, compute_slots=self.streams) as pipe:
-                frames = pipe.map(lambda ctx, job: one(*job), todo, costs=costs)
+            try:
+                with Pipeline(streams=self.streams + 1, compute_slots=self.streams) as pipe:
+                    frames = pipe.map(lambda ctx, job: one(*job), todo, costs=costs)
+            except BaseException:
+                writer.close(quiet=True)
+                raise
         else:
             frames = [one(*job) for job in todo]
+        writer.close()
         growth_frames = [f for f in frames if f is not None]
         if growth_frames:
             pd.concat(growth_frames).to_csv(os.path.join(tmap_dir, tmap_prefix + "_g.txt"), sep="\t",

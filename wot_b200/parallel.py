@@ -86,11 +86,14 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
     keep_growth = model.ot_config.get("growth_iters", 1) > 1
     frames = {}
 
+    _io.check_output_format(output_file_format)
+    writer = _io.TmapWriter(output_file_format)
+
     def one(k):
         tmap = model.compute_transport_map(*day_pairs[k], cost_matrix=cost_matrices[k])
         if tmap is None:
             return None
-        _io.write_dataset(tmap, files[k], output_format=output_file_format)
+        writer.write(tmap, files[k])
         return tmap.obs if keep_growth else None
 
     from .ot import optimal_transport as _ot
@@ -103,6 +106,7 @@ def compute_all_transport_maps(model, tmap_out="tmaps", overwrite=True, output_f
             got = pipe.map(lambda ctx, k: one(k), mine, costs=[cost_of[k] for k in mine])
     else:
         got = [one(k) for k in mine]
+    writer.close()
     for k, obs in zip(mine, got):
         if obs is not None:
             frames[k] = obs
