@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink every day by this factor (debugging)")
     ap.add_argument("--kernel", default="online", choices=["stored", "online", "online_simt"])
     ap.add_argument("--cpu-cells", type=int, default=3200, help="cells/day of the bounded CPU sample (~10 s)")
+    ap.add_argument("--api-pairs", type=int, default=6, help="day-pairs of the e2e_api leg (public OTModel API + .h5ad files)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3 / c5 / e2e_api / row_sharded blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=None,
                     help="day-pairs in flight per GPU, each on its own CUDA stream (wot_b200.pipeline)")
@@ -325,19 +327,221 @@ def online_pass_roofline(ctx, torch, I, J, reps=20):
                                                2, reps, P(sums), C.byref(ms)))
     _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak)))
     achieved = I * J / (ms.value * 1e-3) / 1e12
+    traffic, traffic_src = measured_traffic("k_online_tc", 4937728, "ncu --set full, profiles/r1t_k_online_tc_ncu_full.txt: dram "
+                                            "bytes per launch at 12486x12405 (operands only; nothing of size I*J exists)")
     return {
+        "traffic": traffic, "traffic_source": traffic_src,
         "bound": "mufu", "achieved": achieved, "peak": peak.value / 1e12, "unit": "Texp/s",
         "frac": achieved / (peak.value / 1e12),
-        "traffic": 4940544, "traffic_source": "ncu --set full, profiles/r1e_k_online_tc_ncu_full.txt: dram bytes per launch "
-                                              "at 12486x12405 (operands only; nothing of size I*J exists)",
         "peak_source": "MUFU.EX2 rate measured on this GPU (wotb_bench_mufu_dev: 16 independent ex2 chains per thread, "
                        "32 warps per SM); nominal 16/clk/SM x 148 x 1.965 GHz = 4.65 T/s",
         "kernel": "k_online_tc (tcgen05 cross term + offsets in TMEM, exp2 split between MUFU.EX2 and packed FMA-pipe "
                   "polynomial, one half-iteration per launch)",
         "shape": [I, J], "algorithmic_exp_per_launch": I * J, "pass_ms": ms.value,
+        "algorithmic_operand_bytes_per_launch": (((I + 255) // 256 * 256) + ((J + 255) // 256 * 256)) * 192,
         "note": "achieved counts exponentials evaluated per second; entries moved to the FMA pipe make fractions above "
                 "1.0 possible in principle",
     }
+
+
+def measured_traffic(key, fallback_bytes, fallback_source):
+    """DRAM bytes per launch of the dominant kernel from the round's `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/summarize_ncu.py traffic); a profiler cannot run inside the timed
+    region, so the figure is per round, not per run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            rec = json.load(fh)[key]
+        return rec["dram_bytes_per_launch"], rec["source"]
+    except Exception:
+        return fallback_bytes, fallback_source
+
+
+def guarded(fn):
+    """The extra blocks must never take the headline line down with them."""
+    try:
+        return fn()
+    except Exception as exc:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+
+def c3_block(torch, local_rank, mufu_peak, hbm_peak, n=50000):
+    """BASELINE.json configs[2]: one 50k x 50k pair (seed 2), stored-K vs online-K on one GPU, defaults."""
+    from wot_b200 import _lib, synthetic
+    x0, x1, growth = synthetic.day_pair_coords(n, n, d=D, seed=2)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream()
+    ctx = _lib.Context(local_rank, stream.cuda_stream)
+    lib, h = ctx.lib, ctx.handle
+    out = {"shape": [n, n]}
+    with torch.cuda.stream(stream):
+        X0, X1, G = (torch.from_numpy(a).to(dev) for a in (x0, x1, growth))
+        P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        med = C.c_double()
+        t0 = time.perf_counter()
+        _lib.check(lib.wotb_cost_median_dev(h, P(X0), n, P(X1), n, D, None, C.byref(med)))
+        out["median_s"] = time.perf_counter() - t0
+        res = {}
+        for kernel in ("online", "stored"):
+            prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_STORED if kernel == "stored" else
+                                   _lib.KERNEL_ONLINE, **DEFAULTS)
+            f = torch.empty(n, dtype=torch.float64, device=dev)
+            g = torch.empty(n, dtype=torch.float64, device=dev)
+            rows = torch.empty(n, dtype=torch.float64, device=dev)
+            info = _lib.Info()
+            if kernel == "stored":
+                ld = (n + 31) // 32 * 32
+                Cm = torch.empty(n * ld, dtype=torch.float32, device=dev)
+                _lib.check(lib.wotb_cost_matrix_dev(h, P(X0), n, P(X1), n, D, None, med.value, P(Cm), ld, _lib.F32))
+                _lib.check(lib.wotb_sinkhorn_stored_dev(h, P(Cm), ld, n, n, P(G), C.byref(prm), P(f), P(g), P(rows),
+                                                        C.byref(info)))
+                del Cm
+            else:
+                _lib.check(lib.wotb_sinkhorn_online_dev(h, P(X0), n, P(X1), n, D, med.value, P(G), C.byref(prm), P(f),
+                                                        P(g), P(rows), C.byref(info)))
+            i = info.as_dict()
+            sec = i["gpu_ms"] * 1e-3
+            rec = {"iters": i["iters"], "batches": i["batches"], "solve_ms": i["gpu_ms"], "iters_per_s": i["iters"] / sec,
+                   "workspace_gb": lib.wotb_workspace_bytes(h) / 1e9}
+            if kernel == "stored":
+                ld = (n + 31) // 32 * 32
+                sweeps = 1 if n <= 23040 else 2          # rows beyond 23k columns do not fit the fused kernel's ring
+                gbs = sweeps * n * ld * 4 * i["iters"] / sec / 1e9
+                rec.update(hbm_gbs_all_in=gbs, hbm_frac_all_in=gbs / hbm_peak, k_sweeps_per_iter=sweeps)
+            else:
+                texp = 2.0 * n * n * i["iters"] / sec / 1e12
+                rec.update(texp_per_s_all_in=texp, mufu_frac_all_in=texp / mufu_peak)
+            out[kernel] = rec
+            res[kernel] = (f.cpu().numpy(), g.cpu().numpy(), rows.cpu().numpy())
+            lib.wotb_release_workspace(h)
+            torch.cuda.empty_cache()
+    a, b = res["stored"], res["online"]
+    out["online_vs_stored"] = {"max_abs_df_over_eps": float(np.max(np.abs(a[0] - b[0])) / 0.05),
+                               "max_abs_dg_over_eps": float(np.max(np.abs(a[1] - b[1])) / 0.05),
+                               "max_rel_rowsum": float(np.max(np.abs(a[2] - b[2]) / np.abs(a[2]))),
+                               "same_batches": out["stored"]["batches"] == out["online"]["batches"]}
+    out["speedup_online_over_stored"] = out["stored"]["solve_ms"] / out["online"]["solve_ms"]
+    ctx.close()
+    return out
+
+
+def c5_block(local_rank, n=10000):
+    """A slice of BASELINE.json configs[4]: 8 of the 64 (eps, lambda1, lambda2) settings on the 10k x 10k pair
+    (seed 4), two settings in flight (wot_b200.parallel.parameter_sweep)."""
+    from wot_b200 import parallel, synthetic
+    x0, x1, growth = synthetic.day_pair_coords(n, n, d=D, seed=4)
+    grid = [dict(epsilon=e, lambda1=l1, lambda2=l2) for e in (0.01, 0.025, 0.05, 0.1) for l1, l2 in ((1.0, 50.0), (10.0, 10.0))]
+    common = {k: v for k, v in DEFAULTS.items() if k not in ("epsilon", "lambda1", "lambda2")}
+    t0 = time.perf_counter()
+    res = parallel.parameter_sweep(x0, x1, growth, grid, kernel="auto", streams=2, **common)
+    wall = time.perf_counter() - t0
+    iters = sum(r["iters"] for r in res)
+    return {"shape": [n, n], "settings": len(grid), "of": 64, "wall_s": wall, "settings_per_s": len(grid) / wall,
+            "sinkhorn_iters": iters, "iters_per_s": iters / wall,
+            "iters_by_setting": [[r["setting"]["epsilon"], r["setting"]["lambda1"], r["setting"]["lambda2"], r["iters"]] for r in res],
+            "all_converged": all(r["status"] == 0 for r in res)}
+
+
+def e2e_api_block(local_rank, n_pairs, scale):
+    """The workload through the PUBLIC API from expression matrices (1,479 genes, as Notebook 2):
+    OTModel(adata, growth_iters=3).compute_all_transport_maps(..., output_file_format='h5ad') = local PCA on the GPU
+    + cost + 3 solves + float64 coupling to the host + the .h5ad file of every pair (written behind the solves)."""
+    import shutil
+    import tempfile
+
+    import pandas as pd
+    from wot_b200 import h5ad, ot, synthetic
+    from wot_b200._anndata import AnnData
+    sizes = [max(2, int(v * scale)) for v in synthetic.atlas_day_sizes(seed=1)[: n_pairs + 1]]
+    X, day, growth = synthetic.expression_matrix(sizes, n_genes=1479, seed=1)
+    obs = pd.DataFrame({"day": day * 0.5, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    adata = AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])]))
+    model = ot.OTModel(adata, growth_iters=GROWTH_ITERS)
+    tmp = tempfile.mkdtemp(prefix="wotb_bench_")
+    try:
+        walls = []
+        for rep in range(2):                     # the first pass sizes workspaces and the page-locked output pool
+            t0 = time.perf_counter()
+            model.compute_all_transport_maps(tmap_out=os.path.join(tmp, "tmaps"), output_file_format="h5ad")
+            walls.append(time.perf_counter() - t0)
+        files = sorted(f for f in os.listdir(tmp) if f.endswith(".h5ad"))
+        nbytes = sum(os.path.getsize(os.path.join(tmp, f)) for f in files)
+        back = h5ad.read_h5ad(os.path.join(tmp, files[0]), with_x=False)
+        ok = len(files) == n_pairs and list(back["obs"]) == ["g%d" % k for k in range(GROWTH_ITERS + 1)]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"value": n_pairs / walls[1], "unit": "tmaps/s", "pairs": n_pairs, "cells": int(X.shape[0]), "genes": 1479,
+            "wall_s": walls[1], "first_pass_wall_s": walls[0], "files": len(files), "h5ad_bytes": nbytes,
+            "h2d_bytes": int(2 * X.nbytes - X[: sizes[0]].nbytes - X[-sizes[-1]:].nbytes),
+            "files_ok": bool(ok), "includes": "local PCA on the GPU, cost + median, 3 solves per pair, float64 coupling to "
+                                              "pinned host memory, .h5ad files written behind the solves"}
+
+
+def row_sharded_block(torch, dist, rank, world, local_rank, mufu_peak, n=100000):
+    """BASELINE.json configs[3]: ONE 100k x 100k pair (seed 3), online kernel, rows sharded over the ranks, an NCCL
+    all-reduce per Sinkhorn iteration.  Parity: the same solve on one GPU (every rank runs it redundantly), float64
+    blockwise marginals of the returned potentials on sampled rows, the fixed-point equations."""
+    from wot_b200 import _lib, parallel, synthetic
+    x0, x1, growth = synthetic.day_pair_coords(n, n, d=D, seed=3)
+    dev = torch.device("cuda", local_rank)
+    res = parallel.sharded_online_solve(x0, x1, growth, **DEFAULTS)      # warm-up: workspaces, NCCL channels
+    timers = {}
+    res = parallel.sharded_online_solve(x0, x1, growth, timers=timers, **DEFAULTS)
+    info = res["info"]
+    solve_ms = info["gpu_ms"]
+    t = torch.tensor([solve_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    solve_ms = float(t.item())
+    f, g, rowsum = res["f"], res["g"], res["rowsum"]
+    # ---- the same pair on ONE GPU (redundantly on every rank): batch counts must be identical ----
+    ctx = res["ctx"]
+    X0, X1 = res["coords"]
+    Gd = torch.from_numpy(growth).to(dev)
+    P = lambda v: C.c_void_p(v.data_ptr())  # noqa: E731
+    prm = _lib.make_params(solver=_lib.SOLVER_DUALITY_GAP, kernel=_lib.KERNEL_ONLINE, **DEFAULTS)
+    f1 = torch.empty(n, dtype=torch.float64, device=dev)
+    g1 = torch.empty(n, dtype=torch.float64, device=dev)
+    r1 = torch.empty(n, dtype=torch.float64, device=dev)
+    one = _lib.Info()
+    with torch.cuda.stream(res["stream"]):
+        _lib.check(ctx.lib.wotb_sinkhorn_online_dev(ctx.handle, P(X0), n, P(X1), n, D, res["median"], P(Gd), C.byref(prm),
+                                                    P(f1), P(g1), P(r1), C.byref(one)))
+    one = one.as_dict()
+    torch.cuda.synchronize()
+    # ---- float64 blockwise check on sampled rows (torch, independent of the library's kernels) ----
+    rng = np.random.default_rng(5)
+    rows = torch.from_numpy(np.sort(rng.choice(n, 512, replace=False))).to(dev)
+    eps = info["eps_final"]
+    cst = ((X0[rows][:, None, :] - X1[None, :, :]) ** 2).sum(-1) / res["median"] if n <= 20000 else None
+    if cst is None:
+        acc = torch.zeros(len(rows), dtype=torch.float64, device=dev)
+        for c0 in range(0, n, 8192):
+            blk = X1[c0:c0 + 8192]
+            cc = ((X0[rows][:, None, :] - blk[None, :, :]) ** 2).sum(-1) / res["median"]
+            acc += torch.exp((f[rows][:, None] + g[c0:c0 + 8192][None, :] - cc) / eps).sum(1)
+        marg = acc * info["out_scale"]
+    else:
+        marg = torch.exp((f[rows][:, None] + g[None, :] - cst) / eps).sum(1) * info["out_scale"]
+    rel_rowsum = float((torch.abs(rowsum[rows] - marg) / marg).max().item())
+    # unbalanced fixed point (optimal_transport.py:133): row mass = p_i exp(-f_i / lambda1)
+    Gs = Gd[rows]
+    fixed = float((torch.abs(marg * n / n - Gs * torch.exp(-f[rows] / DEFAULTS["lambda1"])) / marg).max().item())
+    iters = info["iters"]
+    sec = solve_ms * 1e-3
+    out = {"shape": [n, n], "n_gpus": world, "iters": iters, "batches": info["batches"], "solve_ms": solve_ms,
+           "iters_per_s": iters / sec, "mufu_frac_aggregate": 2.0 * n * n * iters / sec / 1e12 / (world * mufu_peak),
+           "allreduce_us_per_iter": timers.get("allreduce_us_per_iter"), "allreduce_bytes": timers.get("allreduce_bytes"),
+           "launch_mode": timers.get("mode"),
+           "one_gpu": {"iters": one["iters"], "batches": one["batches"], "solve_ms": one["gpu_ms"]},
+           "speedup_vs_one_gpu": one["gpu_ms"] / solve_ms, "efficiency_vs_one_gpu": one["gpu_ms"] / solve_ms / world,
+           "parity": {"batches_equal_one_gpu": info["batches"] == one["batches"], "iters_equal_one_gpu": iters == one["iters"],
+                      "max_abs_df_over_eps_vs_one_gpu": float(torch.abs(f - f1).max().item() / eps),
+                      "max_abs_dg_over_eps_vs_one_gpu": float(torch.abs(g - g1).max().item() / eps),
+                      "max_rel_rowsum_vs_float64_marginals_512_rows": rel_rowsum,
+                      "max_rel_fixed_point_residual_512_rows": fixed,
+                      "tolerance": 1e-4}}
+    out["parity"]["ok"] = bool(out["parity"]["batches_equal_one_gpu"] and rel_rowsum <= 1e-4 and
+                               out["parity"]["max_abs_df_over_eps_vs_one_gpu"] <= 1e-4)
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -532,8 +736,22 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_steps / t_e2e
     pipe2.close()
     del outs
-    if n_streams > 1:
-        ctx.lib.wotb_set_pdl(0)      # pipe2.close() restored the default; `pipe` (several streams) is still open
+    peak_c = C.c_double()
+    _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak_c)))
+    mufu_peak = peak_c.value / 1e12
+
+    # ---- configs[3] on N > 1 GPUs: one 100k x 100k pair, rows sharded, NCCL all-reduce per iteration ----
+    row_sharded = None
+    if world > 1 and not args.no_extras:
+        for c in pipe.contexts:
+            c.lib.wotb_release_workspace(c.handle)
+        torch.cuda.empty_cache()
+        n_big = max(512, int(100000 * args.scale))
+        try:
+            row_sharded = row_sharded_block(torch, dist, rank, world, local_rank, mufu_peak, n=n_big)
+        except Exception as exc:  # noqa: BLE001 - every rank takes the same path (the solve is collective)
+            row_sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        barrier()
 
     if rank != 0:
         if dist is not None:
@@ -561,13 +779,14 @@ def run_ours(args, rank, world, local_rank):
         kernel = "k_row + k_col (stored-K matvec pair = one Sinkhorn iteration)"
     roofline_stored = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": 615000000, "traffic_source": "ncu --set full, profiles/r1b_k_fused_ncu_full.txt: 3.075 GB read per "
-                                                "5-iteration launch at this shape",
         "peak_source": peak_src, "kernel": kernel,
         "shape": [ri, rj], "algorithmic_bytes_per_launch": alg,
         "fused_iter_ms": ms_fused, "row_ms": ms_row, "col_ms": ms_col,
         "row_gbs": alg / (ms_row * 1e-3) / 1e9, "col_gbs": alg / (ms_col * 1e-3) / 1e9,
     }
+    roofline_stored["traffic"], roofline_stored["traffic_source"] = measured_traffic(
+        "k_fused", 615000000, "ncu --set full, profiles/r1b_k_fused_ncu_full.txt: 3.075 GB read per 5-iteration launch "
+                              "at this shape (round 1 capture)")
     roofline_online = online_pass_roofline(ctx, torch, ri, rj)      # launch mode of the timed region
     if n_streams > 1:
         # one solve at a time launches the passes with programmatic dependent launch (the pipeline turns it off)
@@ -589,14 +808,36 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if not args.no_cpu_baseline:
-        sec, m0, m1, it = cpu_reference_sample(pairs[0], args.cpu_cells, growth_iters=1)
+        cores = host_threads()
+        sec, m0, m1, kind = cpu_reference_sample(pairs[0], args.cpu_cells, growth_iters=1)
         mean_ij = float(np.mean([a * b for a, b, _ in pairs]))
         sec_per_tmap = sec / (m0 * m1) * mean_ij * GROWTH_ITERS
-        cpu = {"value": 1.0 / sec_per_tmap, "unit": "tmaps/s", "cores": blas_threads(), "kind": "port",
-               "sample": "one full reference-port solve (%d iterations, dense primal/dual) of atlas pair 0 subsampled "
-                         "to %dx%d in %.1f s; seconds per entry scaled to the mean atlas pair and growth_iters=3"
-                         % (it, m0, m1, sec),
-               "iters_per_s_at_sample": it / sec}
+        cpu = {"value": 1.0 / sec_per_tmap, "unit": "tmaps/s", "cores": cores, "kind": kind,
+               "sample": "one full solve (cost + duality-gap solver, growth_iters=1) of atlas pair 0 subsampled to %dx%d "
+                         "through the %s in %.1f s; seconds per matrix entry scaled to the mean atlas pair and "
+                         "growth_iters=3 (`--impl reference` times full-size pairs)"
+                         % (m0, m1, "unmodified reference solver (oracle/_ref)" if kind == "reference" else
+                            "NumPy port of the reference (oracle/)", sec)}
+
+    # ---- the other BASELINE configs and the public-API leg (N = 1) ---------------------------------------
+    extras = {}
+    if world == 1 and not args.no_extras:
+        _lib._contexts.pop(local_rank, None)      # `ctx` belongs to the pipeline and dies with it
+        pipe.close()
+        from wot_b200.pipeline import release_idle_contexts
+        for c in list(_lib._contexts.values()):
+            c.lib.wotb_release_workspace(c.handle)
+        release_idle_contexts()
+        torch.cuda.empty_cache()
+        extras["e2e_api"] = guarded(lambda: e2e_api_block(local_rank, args.api_pairs, args.scale))
+        release_idle_contexts()
+        torch.cuda.empty_cache()
+        extras["c5"] = guarded(lambda: c5_block(local_rank, n=max(256, int(10000 * args.scale))))
+        release_idle_contexts()
+        torch.cuda.empty_cache()
+        extras["c3"] = guarded(lambda: c3_block(torch, local_rank, mufu_peak, peak, n=max(256, int(50000 * args.scale))))
+    if row_sharded is not None:
+        extras["row_sharded"] = row_sharded
 
     line = {
         "metric": "day-pair transport maps per second", "value": value, "unit": "tmaps/s",
@@ -604,15 +845,7 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": ("f32 exponent (fp16x3 split on tcgen05) / f64 potentials" if online
                                                  else "f32 K / f64 potentials"),
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "solver": "duality_gap", "kernel": args.kernel, "eps": 0.05, "lambda1": 1,
-                   "lambda2": 50, "l2": ("every pass recomputes I*J = 25M-400M entries from L2-resident operands; nothing is cached "
-                          "between steps (each step is a different day-pair)" if online else
-                          "inputs larger than L2 (K and C are 0.1-1.6 GB per pair)"),
-                   "sharding": "one day-pair per GPU per step, no collective", "scale": args.scale,
-                   "streams": n_streams,
-                   "streams_note": "day-pairs are independent: each GPU keeps `streams` of them in flight on separate "
-                                   "CUDA streams (wot_b200.pipeline) so one fills the other's kernel tails, checks "
-                                   "and copies; a step is still one day-pair"},
+        "config": bench_config(args.kernel, n_streams, args.scale),
         "sinkhorn_iters_per_s": iters_all / t_dev,
         "sinkhorn_iters": int(iters_all),
         "clocks": clocks,
@@ -624,8 +857,10 @@ def run_ours(args, rank, world, local_rank):
         other[0]: other[1],
         "cpu_baseline": cpu,
     }
+    line.update(extras)
     print(json.dumps(line), flush=True)
-    pipe.close()
+    if pipe.contexts:
+        pipe.close()
     if dist is not None:
         dist.destroy_process_group()
 

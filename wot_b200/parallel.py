@@ -254,12 +254,21 @@ def _sweep_solve_gpu(x0, x1, G, growth_iters=1, kernel="online", **params):
 OP_BEGIN_A, OP_BEGIN_B, OP_ROW, OP_COL_PARTIAL, OP_COL_FINISH, OP_GAP_ROWS, OP_CHECK, OP_FINAL_ROWS = range(8)
 
 
-def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, **params):
+def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, use_graph=True, **params):
     """Solve one day-pair with its rows sharded over the ranks of `group` (online kernel, float64 state).
 
     x0 [I,d], x1 [J,d], G [I]: the full arrays on every rank (NumPy or CUDA tensors).  Returns a dict with
     f, g (replicated CUDA tensors), rowsum (replicated), rows=(lo, hi) of this rank, median, info.
     With world_size 1 no collective is issued (the stepping path is then a plain single-GPU solve).
+
+    One batch of the device state machine -- operand repack if epsilon changed, 5 x (row half-step on the own rows,
+    partial column sums, ONE all-reduce, column finish), convergence check -- is captured ONCE as a CUDA graph,
+    NCCL all-reduces included, and replayed until the replicated state says done: between two looks at the state
+    the host issues a single cudaGraphLaunch, so neither Python nor launch latency sits between the passes and the
+    collectives (`use_graph=False` keeps the step-by-step launches).  Every kernel of the sequence is a no-op on
+    the device when its work is not due, so all ranks replay the same graph the same number of times.
+    `timers` (dict, optional) receives allreduce_us_per_iter (CUDA events around 20 all-reduces of the per-iteration
+    payload on the solve's stream), allreduce_bytes and the launch mode.
     """
     import torch
     import torch.distributed as dist
@@ -288,7 +297,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         median = params.pop("median", None)
         if median is None:
-            # every rank runs the exact select on the full problem (6 recompute passes; cheap next to the
+            # every rank runs the exact select on the full problem (3 recompute passes; cheap next to the
             # solve) so the value is bit-identical everywhere without a collective
             med = C.c_double()
             _lib.check(lib.wotb_cost_median_dev(h, P(X0), n_i, P(X1), n_j, d, None, C.byref(med)))
@@ -310,24 +319,44 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                 dist.all_reduce(exch[:n], op=dist.ReduceOp.SUM, group=group)
 
         slots = 5 if solver == _lib.SOLVER_DUALITY_GAP else 10
+
+        def batch():
+            step(OP_BEGIN_A)
+            if solver == _lib.SOLVER_DUALITY_GAP:
+                reduce(n_i)
+            step(OP_BEGIN_B)
+            for _ in range(slots):
+                step(OP_ROW)             # a for this rank's rows (+ their row sums, for the lazy gap check)
+                step(OP_COL_PARTIAL)     # needs only this rank's a: no exchange in between
+                reduce(2 * n_i + n_j)    # ONE all-reduce per iteration: gathered a | row sums | column sums
+                step(OP_COL_FINISH)
+            step(OP_CHECK)
+
         info, done = _lib.Info(), C.c_int32(0)
+
+        def state():
+            _lib.check(lib.wotb_online_state(solve, C.byref(info), C.byref(done)))
+            return bool(done.value)
+
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        ev[0].record(stream)
+        graph = None
         try:
-            while True:
-                step(OP_BEGIN_A)
-                if solver == _lib.SOLVER_DUALITY_GAP:
-                    reduce(n_i)
-                step(OP_BEGIN_B)
-                for _ in range(slots):
-                    step(OP_ROW)             # a for this rank's rows (+ their row sums, for the lazy gap check)
-                    step(OP_COL_PARTIAL)     # needs only this rank's a: no exchange in between
-                    reduce(2 * n_i + n_j)    # ONE all-reduce per iteration: gathered a | row sums | column sums
-                    step(OP_COL_FINISH)
-                step(OP_CHECK)
-                _lib.check(lib.wotb_online_state(solve, C.byref(info), C.byref(done)))
-                if done.value:
-                    break
+            if world > 1:
+                reduce(n_i)                       # NCCL communicator and channels exist before timing / capture
+                exch.zero_()
+            ev[0].record(stream)
+            batch()                               # first batch eagerly: sizes the lazily grown workspaces
+            finished = state()
+            if use_graph and not finished:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                    batch()
+            while not finished:
+                if graph is not None:
+                    graph.replay()
+                else:
+                    batch()
+                finished = state()
             step(OP_FINAL_ROWS)
             reduce(n_i)
             rowsum = exch[:n_i].clone()
@@ -335,12 +364,27 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
             ev[1].synchronize()
             lo, hi = C.c_int64(), C.c_int64()
             _lib.check(lib.wotb_online_rows(solve, C.byref(lo), C.byref(hi)))
+            if timers is not None:
+                timers["mode"] = "cuda graph per batch (NCCL captured)" if graph is not None else "stepwise launches"
+                timers["allreduce_bytes"] = (2 * n_i + n_j) * 8
+                if world > 1:
+                    probe = torch.zeros(2 * n_i + n_j, dtype=torch.float64, device=dev)
+                    te = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                    for _ in range(3):
+                        dist.all_reduce(probe, op=dist.ReduceOp.SUM, group=group)
+                    te[0].record(stream)
+                    for _ in range(20):
+                        dist.all_reduce(probe, op=dist.ReduceOp.SUM, group=group)
+                    te[1].record(stream)
+                    te[1].synchronize()
+                    timers["allreduce_us_per_iter"] = te[0].elapsed_time(te[1]) * 1e3 / 20
         finally:
+            del graph
             lib.wotb_online_close(solve)
         out_info = info.as_dict()
         out_info["gpu_ms"] = ev[0].elapsed_time(ev[1])
     return {"f": f, "g": g, "rowsum": rowsum, "rows": (lo.value, hi.value), "median": median, "info": out_info,
-            "ctx": ctx, "coords": (X0, X1)}
+            "ctx": ctx, "coords": (X0, X1), "stream": stream}
 
 
 def local_coupling_rows(result, out_dtype=np.float64):
