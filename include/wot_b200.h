@@ -227,16 +227,29 @@ void wotb_online_close(void *solve);
 
 /* ---- a coupling applied to populations without materialising it ------------------
  * Replaces the products of TransportMapModel.push_forward / pull_back, wot/tmap/transport_map_model.py:290
- * (p @ tmap.X) and :356 (tmap.X @ p.T): the coupling of a finished solve is fully described by the local-PCA
- * coordinates, the median, the potentials f, g, eps_final and out_scale (wotb_info), so
+ * (p @ tmap.X) and :356 (tmap.X @ p.T), where p stacks ALL populations (np.vstack, :285, :351): the coupling of a
+ * finished solve is fully described by the local-PCA coordinates, the median, the potentials f, g, eps_final and
+ * out_scale (wotb_info), so
  *   forward = 1:  out[k, j] = sum_i p[k, i] tmap[i, j]     p [n_pop, I] -> out [n_pop, J]
  *   forward = 0:  out[k, i] = sum_j tmap[i, j] p[k, j]     p [n_pop, J] -> out [n_pop, I]
- * is one pass of the online kernel per population (weights enter as log2 p in the exponent offsets; p >= 0,
- * as wot.Population measures are).  Host pointers, float64; scale_host as in wotb_transport_map_from_coords_host. */
+ * is computed tile by tile in float64: one exponential per coupling entry, then one FP64 FMA per population (8
+ * populations per sweep over the coupling); partial sums are added in a fixed order (deterministic).  Populations
+ * may have any sign.  Host pointers, float64; scale_host as in wotb_transport_map_from_coords_host. */
 int wotb_coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int32_t d,
                              const double *scale_host, double median, const double *f_host, const double *g_host,
                              double eps_final, double out_scale, int32_t forward, const double *p_host, int32_t n_pop,
                              double *out_host);
+
+/* ---- sampling cell pairs from a coupling ------------------------------------------
+ * Replaces the draw of interpolate_with_ot, wot/ot/util.py:140-146 (np.random.choice over the flattened
+ * p = tmap / colsum^(1 - frac)): for sample s the caller gives the row rows[s] it fell into and the mass
+ * targets[s] that remains inside that row (both found on the row masses sum_j tmap[i, j] w[j], which
+ * wotb_coupling_apply_host(forward = 0, p = w) returns); cols[s] receives the first column j whose running sum
+ * sum_{j' <= j} tmap[rows[s], j'] w[j'] exceeds targets[s] (float64, column order, like the flattened cumsum). */
+int wotb_coupling_sample_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int32_t d,
+                              const double *scale_host, double median, const double *f_host, const double *g_host,
+                              double eps_final, double out_scale, const double *w_host, const int64_t *rows_host,
+                              const double *targets_host, int64_t n_samples, int64_t *cols_host);
 
 /* Measurement hook for bench.py: average device time (ms, CUDA events on the context's stream) of one
  * row-pass and one column-pass launch of the stored-K matvec kernels on an I x J kernel matrix. */

@@ -621,8 +621,9 @@ def test_implicit_transport_map_push_forward_pull_back(ot):
     # normalised push-forward then pull-back of a cell set, as TransportMapModel.ancestors / descendants chain them
     q = imp.push_forward(p_rows[1], normalize=True)
     np.testing.assert_allclose(q, (p_rows[1] @ T) / (p_rows[1] @ T).sum(), rtol=RTOL)
+    np.testing.assert_allclose(imp.push_forward(-p_rows[0]), -(p_rows[0] @ T), rtol=RTOL)   # any sign (float64 apply)
     with pytest.raises(ValueError):
-        imp.push_forward(-p_rows[0])
+        imp.push_forward(np.ones(701))
 
 
 @pytest.mark.parametrize("kernel", ["stored", "online", "online_simt"])

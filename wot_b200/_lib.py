@@ -59,6 +59,8 @@ SIGNATURES = {
     "wotb_set_pdl": (None, [C.c_int32]),
     "wotb_coupling_apply_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_double, _P, _P, C.c_double,
                                            C.c_double, C.c_int32, _P, C.c_int32, _P]),
+    "wotb_coupling_sample_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_double, _P, _P, C.c_double,
+                                            C.c_double, _P, _P, _P, C.c_int64, _P]),
     "wotb_pca_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                 _P, _P]),
     "wotb_cost_median_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, C.POINTER(_D)]),

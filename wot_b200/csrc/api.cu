@@ -75,6 +75,10 @@ int cost_to_f32(wotb_ctx *, const double *, int64_t, int64_t, int64_t, float *, 
 int coupling(wotb_ctx *, const float *, int64_t, int64_t, int64_t, const double *, const double *, double, double,
              void *, int64_t, int, double *, cudaStream_t);
 int scale_into(wotb_ctx *, const double *, int64_t, int, const double *, double *);
+int coupling_apply(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *, const double *,
+                   double, double, int, const double *, int, double *);
+int coupling_sample(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *, const double *,
+                    double, double, const double *, const long long *, const double *, int64_t, long long *);
 // solver.cu (online_pass.cuh)
 struct OnlineSolve;
 int online_open(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
@@ -232,27 +236,34 @@ static int finish_host_outputs(wotb_ctx *ctx, int64_t I, int64_t J, const HostVe
 }
 
 
-// ---- coupling applied to populations without materialising it ---------------------------------
-// tmap_ij = exp((f_i + g_j - C_ij)/eps) * out_scale  (SURVEY 8 a-note) in base 2 with C_ij = |x_i - y_j|^2 / median:
-//   log2 tmap_ij = [c1 f_i - c2 |x_i|^2] + [c1 g_j - c2 |y_j|^2 + log2 out_scale] + 2 c2 <x_i, y_j>,  c1 = log2(e)/eps, c2 = c1/median
-// off_a belongs to the side that is summed INTO (out), off_b to the side summed OVER (in), which also carries the
-// population weights log2 p.
-__global__ void k_apply_offsets(const double *__restrict__ x_out, int n_out, const double *__restrict__ pot_out,
-                                const double *__restrict__ x_in, int n_in, const double *__restrict__ pot_in,
-                                const double *__restrict__ p_in, int d, double c1, double c2, double log2_scale,
-                                double *__restrict__ off_out, double *__restrict__ off_in) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_out) {
-        double n2 = 0.0;
-        for (int k = 0; k < d; ++k) n2 = fma(x_out[(size_t)i * d + k], x_out[(size_t)i * d + k], n2);
-        off_out[i] = c1 * pot_out[i] - c2 * n2;
-    }
-    if (i < n_in) {
-        double n2 = 0.0;
-        for (int k = 0; k < d; ++k) n2 = fma(x_in[(size_t)i * d + k], x_in[(size_t)i * d + k], n2);
-        const double w = p_in[i];
-        off_in[i] = w > 0.0 ? c1 * pot_in[i] - c2 * n2 + log2_scale + log2(w) : -INFINITY;
-    }
+// ---- coupling applied to populations / sampled without materialising it ------------------
+// Stages the description of a finished solve (coordinates, scale, potentials) on the device; x0s / x1s are the
+// coordinates multiplied by `scale` (the arithmetic of ot_model.py:245-247).
+struct StagedCoupling {
+    double *x0s, *x1s, *f, *g;
+    char *extra;
+};
+
+static int stage_coupling(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int d,
+                          const double *scale_host, const double *f_host, const double *g_host, size_t extra_bytes,
+                          StagedCoupling *sc) {
+    cudaStream_t st = ctx->stream;
+    const size_t nx0 = (size_t)round_up(I * d, 32) * 8, nx1 = (size_t)round_up(J * d, 32) * 8, nsc = (size_t)round_up(d, 32) * 8;
+    const size_t nI = (size_t)round_up(I, 32) * 8, nJ = (size_t)round_up(J, 32) * 8;
+    WOTB_TRY(ctx->hX.reserve(2 * (nx0 + nx1) + nsc + nI + nJ + extra_bytes + 256));
+    char *b = ctx->hX.as<char>();
+    double *x0 = (double *)b, *x1 = (double *)(b + nx0), *scl = (double *)(b + nx0 + nx1);
+    sc->x0s = (double *)(b + nx0 + nx1 + nsc), sc->x1s = (double *)(b + 2 * nx0 + nx1 + nsc);
+    char *v = b + 2 * (nx0 + nx1) + nsc;
+    sc->f = (double *)v, sc->g = (double *)(v + nI), sc->extra = v + nI + nJ;
+    WOTB_CUDA(cudaMemcpyAsync(x0, x0_host, (size_t)I * d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(x1, x1_host, (size_t)J * d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(sc->f, f_host, (size_t)I * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(sc->g, g_host, (size_t)J * 8, cudaMemcpyHostToDevice, st));
+    if (scale_host) WOTB_CUDA(cudaMemcpyAsync(scl, scale_host, (size_t)d * 8, cudaMemcpyHostToDevice, st));
+    WOTB_TRY(scale_into(ctx, x0, I, d, scale_host ? scl : nullptr, sc->x0s));
+    WOTB_TRY(scale_into(ctx, x1, J, d, scale_host ? scl : nullptr, sc->x1s));
+    return WOTB_OK;
 }
 
 static int coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int d,
@@ -264,35 +275,36 @@ static int coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, 
     WOTB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t n_in = forward ? I : J, n_out = forward ? J : I;
-    const size_t nx0 = (size_t)round_up(I * d, 32) * 8, nx1 = (size_t)round_up(J * d, 32) * 8, nsc = (size_t)round_up(d, 32) * 8;
-    const size_t nI = (size_t)round_up(I, 32) * 8, nJ = (size_t)round_up(J, 32) * 8;
-    const size_t nin = forward ? nI : nJ, nout = forward ? nJ : nI;
-    WOTB_TRY(ctx->hX.reserve(2 * (nx0 + nx1) + nsc + nI + nJ + 2 * nin + 2 * nout + 256));
-    char *b = ctx->hX.as<char>();
-    double *x0 = (double *)b, *x1 = (double *)(b + nx0), *sc = (double *)(b + nx0 + nx1);
-    double *xs0 = (double *)(b + nx0 + nx1 + nsc), *xs1 = (double *)(b + 2 * nx0 + nx1 + nsc);
-    char *v = b + 2 * (nx0 + nx1) + nsc;
-    double *f = (double *)v, *g = (double *)(v + nI), *p = (double *)(v + nI + nJ), *off_in = (double *)(v + nI + nJ + nin);
-    double *off_out = (double *)(v + nI + nJ + 2 * nin), *sums = (double *)(v + nI + nJ + 2 * nin + nout);
-    WOTB_CUDA(cudaMemcpyAsync(x0, x0_host, (size_t)I * d * 8, cudaMemcpyHostToDevice, st));
-    WOTB_CUDA(cudaMemcpyAsync(x1, x1_host, (size_t)J * d * 8, cudaMemcpyHostToDevice, st));
-    WOTB_CUDA(cudaMemcpyAsync(f, f_host, (size_t)I * 8, cudaMemcpyHostToDevice, st));
-    WOTB_CUDA(cudaMemcpyAsync(g, g_host, (size_t)J * 8, cudaMemcpyHostToDevice, st));
-    if (scale_host) WOTB_CUDA(cudaMemcpyAsync(sc, scale_host, (size_t)d * 8, cudaMemcpyHostToDevice, st));
-    WOTB_TRY(scale_into(ctx, x0, I, d, scale_host ? sc : nullptr, xs0));
-    WOTB_TRY(scale_into(ctx, x1, J, d, scale_host ? sc : nullptr, xs1));
-    const double c1 = 1.4426950408889634 / eps_final, c2 = c1 / median;
-    const double *x_out = forward ? xs1 : xs0, *x_in = forward ? xs0 : xs1;
-    const double *pot_out = forward ? g : f, *pot_in = forward ? f : g;
-    const int impl = d <= 46 ? 2 : 0;  // tcgen05 pass when the coordinates fit its K budget, SIMT FP32 otherwise
-    for (int k = 0; k < n_pop; ++k) {
-        WOTB_CUDA(cudaMemcpyAsync(p, p_host + (size_t)k * n_in, (size_t)n_in * 8, cudaMemcpyHostToDevice, st));
-        const int64_t n = n_in > n_out ? n_in : n_out;
-        k_apply_offsets<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(x_out, (int)n_out, pot_out, x_in, (int)n_in, pot_in, p, d, c1, c2,
-                                                                 log2(out_scale), off_out, off_in);
-        WOTB_TRY(online_rowsums(ctx, x_out, n_out, x_in, n_in, d, sqrt(2.0 * c2), off_out, off_in, impl, 0, sums, nullptr));
-        WOTB_CUDA(cudaMemcpyAsync(out_host + (size_t)k * n_out, sums, (size_t)n_out * 8, cudaMemcpyDeviceToHost, st));
-    }
+    const size_t np_in = (size_t)round_up((int64_t)n_pop * n_in, 32) * 8, np_out = (size_t)round_up((int64_t)n_pop * n_out, 32) * 8;
+    StagedCoupling sc;
+    WOTB_TRY(stage_coupling(ctx, x0_host, I, x1_host, J, d, scale_host, f_host, g_host, np_in + np_out, &sc));
+    double *p = (double *)sc.extra, *out = (double *)(sc.extra + np_in);
+    WOTB_CUDA(cudaMemcpyAsync(p, p_host, (size_t)n_pop * n_in * 8, cudaMemcpyHostToDevice, st));
+    WOTB_TRY(coupling_apply(ctx, sc.x0s, I, sc.x1s, J, d, median, sc.f, sc.g, eps_final, out_scale, forward, p, n_pop, out));
+    WOTB_CUDA(cudaMemcpyAsync(out_host, out, (size_t)n_pop * n_out * 8, cudaMemcpyDeviceToHost, st));
+    WOTB_CUDA(cudaStreamSynchronize(st));
+    return WOTB_OK;
+}
+
+static int coupling_sample_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int d,
+                                const double *scale_host, double median, const double *f_host, const double *g_host,
+                                double eps_final, double out_scale, const double *w_host, const int64_t *rows_host,
+                                const double *targets_host, int64_t n_samples, int64_t *cols_host) {
+    WOTB_REQUIRE(ctx && x0_host && x1_host && f_host && g_host && w_host && rows_host && targets_host && cols_host, "NULL argument");
+    WOTB_REQUIRE(I >= 1 && J >= 1 && d >= 1 && n_samples >= 0 && median > 0 && eps_final > 0 && out_scale > 0, "bad arguments");
+    for (int64_t s = 0; s < n_samples; ++s) WOTB_REQUIRE(rows_host[s] >= 0 && rows_host[s] < I, "row index out of range");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t nJ = (size_t)round_up(J, 32) * 8, nS = (size_t)round_up(n_samples + 1, 32) * 8;
+    StagedCoupling sc;
+    WOTB_TRY(stage_coupling(ctx, x0_host, I, x1_host, J, d, scale_host, f_host, g_host, nJ + 3 * nS, &sc));
+    double *w = (double *)sc.extra, *targets = (double *)(sc.extra + nJ + nS);
+    long long *rows = (long long *)(sc.extra + nJ), *cols = (long long *)(sc.extra + nJ + 2 * nS);
+    WOTB_CUDA(cudaMemcpyAsync(w, w_host, (size_t)J * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(rows, rows_host, (size_t)n_samples * 8, cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemcpyAsync(targets, targets_host, (size_t)n_samples * 8, cudaMemcpyHostToDevice, st));
+    WOTB_TRY(coupling_sample(ctx, sc.x0s, I, sc.x1s, J, d, median, sc.f, sc.g, eps_final, out_scale, w, rows, targets, n_samples, cols));
+    WOTB_CUDA(cudaMemcpyAsync(cols_host, cols, (size_t)n_samples * 8, cudaMemcpyDeviceToHost, st));
     WOTB_CUDA(cudaStreamSynchronize(st));
     return WOTB_OK;
 }
@@ -611,6 +623,14 @@ int wotb_coupling_apply_host(wotb_ctx *ctx, const double *x0_host, int64_t I, co
                              double *out_host) {
     return coupling_apply_host(ctx, x0_host, I, x1_host, J, d, scale_host, median, f_host, g_host, eps_final, out_scale,
                                forward, p_host, n_pop, out_host);
+}
+
+int wotb_coupling_sample_host(wotb_ctx *ctx, const double *x0_host, int64_t I, const double *x1_host, int64_t J, int32_t d,
+                              const double *scale_host, double median, const double *f_host, const double *g_host,
+                              double eps_final, double out_scale, const double *w_host, const int64_t *rows_host,
+                              const double *targets_host, int64_t n_samples, int64_t *cols_host) {
+    return coupling_sample_host(ctx, x0_host, I, x1_host, J, d, scale_host, median, f_host, g_host, eps_final, out_scale,
+                                w_host, rows_host, targets_host, n_samples, cols_host);
 }
 
 int wotb_pinned_alloc(size_t bytes, void **out) {

@@ -504,4 +504,224 @@ int coupling_online(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1
     return WOTB_OK;
 }
 
+// ---- a coupling applied to several populations at once, never materialised --------------------------
+// Reference: TransportMapModel.push_forward / pull_back, wot/tmap/transport_map_model.py:290 (p @ tmap.X) and :356
+// (tmap.X @ p.T), where p stacks ALL populations (np.vstack, :285 / :351).  tmap_ij = exp((f_i + g_j - C_ij)/eps) * scale is
+// evaluated tile by tile in float64 exactly as k_coupling_online does -- ONE exponential per entry -- and every entry
+// is then used NP times: out[k, o] += tmap[.,.] * p[k, .] (FP64 FMAs, which are cheap next to the distance and the
+// exponential).  A CTA owns one 64-wide tile of the OUT side and a contiguous range of tiles of the side that is
+// summed over; the partial results of the ranges are added in a fixed order by k_apply_reduce: deterministic.
+constexpr int kApplyNP = 8;  // populations per sweep over the coupling
+
+template <bool FORWARD>
+__global__ void __launch_bounds__(kTileThreads)
+    k_apply_multi(const double *__restrict__ x0, long long I, const double *__restrict__ x1, long long J, int d,
+                  const double *__restrict__ f, const double *__restrict__ g, double inv_median, double inv_eps, double scale,
+                  const double *__restrict__ P, long long ldp, int np, double *__restrict__ part, long long n_out) {
+    __shared__ double xs[kChunk][kTilePad];
+    __shared__ double ys[kChunk][kTilePad];
+    __shared__ double pw[kApplyNP][kTile];
+    __shared__ double red[16][kTile];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long n_in = FORWARD ? I : J;
+    const long long tiles_in = (n_in + kTile - 1) / kTile;
+    const long long o0 = (long long)blockIdx.x * kTile;  // first out entry of this CTA
+    const long long t_lo = tiles_in * blockIdx.y / gridDim.y, t_hi = tiles_in * (blockIdx.y + 1) / gridDim.y;
+    double acc_out[kApplyNP][4];
+#pragma unroll
+    for (int k = 0; k < kApplyNP; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc_out[k][c] = 0.0;
+    for (long long t = t_lo; t < t_hi; ++t) {
+        const long long in0 = t * kTile;
+        const long long i0 = FORWARD ? in0 : o0, j0 = FORWARD ? o0 : in0;
+        double acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+        for (int k0 = 0; k0 < d; k0 += kChunk) {
+            const int kc = min(kChunk, d - k0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < kTile * kChunk; e += kTileThreads) {
+                const int k = e % kChunk, r = e / kChunk;
+                const long long gi = i0 + r, gj = j0 + r;
+                xs[k][r] = (k < kc && gi < I) ? x0[gi * d + k0 + k] : 0.0;
+                ys[k][r] = (k < kc && gj < J) ? x1[gj * d + k0 + k] : 0.0;
+            }
+            if (k0 == 0) {
+                for (int e = threadIdx.x; e < kApplyNP * kTile; e += kTileThreads) {
+                    const int k = e / kTile, r = e % kTile;
+                    pw[k][r] = (k < np && in0 + r < n_in) ? P[(long long)k * ldp + in0 + r] : 0.0;
+                }
+            }
+            __syncthreads();
+            for (int k = 0; k < kc; ++k) {
+                double xv[4], yv[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) xv[r] = xs[k][ty * 4 + r];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) yv[c] = ys[k][tx * 4 + c];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double df = __dsub_rn(xv[r], yv[c]);
+                        acc[r][c] = __dadd_rn(acc[r][c], __dmul_rn(df, df));
+                    }
+            }
+        }
+        // entries of the coupling (zero outside the matrix), then NP fused multiply-adds each
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const long long i = i0 + ty * 4 + r;
+            const double fi = i < I ? f[i] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const long long j = j0 + tx * 4 + c;
+                const double e = (i < I && j < J) ? exp((fi + g[j] - acc[r][c] * inv_median) * inv_eps) * scale : 0.0;
+#pragma unroll
+                for (int k = 0; k < kApplyNP; ++k) {
+                    if (FORWARD)
+                        acc_out[k][c] = fma(e, pw[k][ty * 4 + r], acc_out[k][c]);   // out = column j, weight of row i
+                    else
+                        acc_out[k][r] = fma(e, pw[k][tx * 4 + c], acc_out[k][r]);   // out = row i, weight of column j
+                }
+            }
+        }
+    }
+    // reduce over the 16 threads that share an out entry (fixed order), one population at a time
+    for (int k = 0; k < np; ++k) {
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            if (FORWARD)
+                red[ty][tx * 4 + c] = acc_out[k][c];
+            else
+                red[tx][ty * 4 + c] = acc_out[k][c];
+        }
+        __syncthreads();
+        if (threadIdx.x < kTile && o0 + threadIdx.x < n_out) {
+            double sum = 0.0;
+            for (int q = 0; q < 16; ++q) sum += red[q][threadIdx.x];
+            part[((long long)blockIdx.y * np + k) * n_out + o0 + threadIdx.x] = sum;
+        }
+    }
+}
+
+__global__ void k_apply_reduce(const double *__restrict__ part, int n_split, int np, long long n_out, double *__restrict__ out,
+                               long long ldo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)np * n_out) return;
+    const long long k = idx / n_out, o = idx % n_out;
+    double sum = 0.0;
+    for (int sp = 0; sp < n_split; ++sp) sum += part[((long long)sp * np + k) * n_out + o];
+    out[k * ldo + o] = sum;
+}
+
+// out[k, :] for k < n_pop (device pointers; P [n_pop, n_in] row-major, out [n_pop, n_out]); x0, x1 already scaled
+int coupling_apply(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
+                   const double *f, const double *g, double eps, double out_scale, int forward, const double *P, int n_pop,
+                   double *out) {
+    const int64_t n_in = forward ? I : J, n_out = forward ? J : I;
+    const int tiles_out = (int)cdiv(n_out, kTile), tiles_in = (int)cdiv(n_in, kTile);
+    int n_split = (int)cdiv((int64_t)ctx->sm_count * 3, tiles_out);
+    if (n_split > tiles_in) n_split = tiles_in;
+    if (n_split < 1) n_split = 1;
+    WOTB_TRY(ctx->part.reserve((size_t)n_split * kApplyNP * n_out * 8));
+    double *part = ctx->part.as<double>();
+    const dim3 grid(tiles_out, n_split);
+    for (int k0 = 0; k0 < n_pop; k0 += kApplyNP) {
+        const int np = n_pop - k0 < kApplyNP ? n_pop - k0 : kApplyNP;
+        if (forward)
+            k_apply_multi<true><<<grid, kTileThreads, 0, ctx->stream>>>(x0, I, x1, J, d, f, g, 1.0 / median, 1.0 / eps, out_scale,
+                                                                        P + (size_t)k0 * n_in, n_in, np, part, n_out);
+        else
+            k_apply_multi<false><<<grid, kTileThreads, 0, ctx->stream>>>(x0, I, x1, J, d, f, g, 1.0 / median, 1.0 / eps, out_scale,
+                                                                         P + (size_t)k0 * n_in, n_in, np, part, n_out);
+        k_apply_reduce<<<(unsigned)cdiv((int64_t)np * n_out, 256), 256, 0, ctx->stream>>>(part, n_split, np, n_out,
+                                                                                          out + (size_t)k0 * n_out, n_out);
+    }
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+// ---- sampling cell pairs from a coupling --------------------------------------------------------------
+// Reference: interpolate_with_ot, wot/ot/util.py:140-147: p = tmap / colsum^(1 - frac), flattened, normalised;
+// np.random.choice(I*J, p=p, size) = searchsorted(cumsum(p), uniform samples).  The flattened cumulative sum is walked
+// hierarchically: the caller finds the ROW of every sample on the row masses (pull-back of the column weights,
+// coupling_apply) and hands over (row, remaining mass t); one CTA per sample evaluates that row of the weighted
+// coupling in float64 in column order and returns the first column whose running sum exceeds t.
+constexpr int kSampleThreads = 256;
+
+__global__ void __launch_bounds__(kSampleThreads)
+    k_coupling_sample(const double *__restrict__ x0, long long I, const double *__restrict__ x1, long long J, int d,
+                      const double *__restrict__ f, const double *__restrict__ g, double inv_median, double inv_eps, double scale,
+                      const double *__restrict__ w, const long long *__restrict__ rows, const double *__restrict__ targets,
+                      long long *__restrict__ cols) {
+    __shared__ double xi[256];
+    __shared__ double seg[kSampleThreads + 1];
+    __shared__ int pick;
+    const long long i = rows[blockIdx.x];
+    const double t = targets[blockIdx.x];
+    for (int k = threadIdx.x; k < d; k += kSampleThreads) xi[k] = x0[i * d + k];
+    __syncthreads();
+    const double fi = f[i];
+    const long long per = (J + kSampleThreads - 1) / kSampleThreads;
+    const long long j_lo = per * threadIdx.x, j_hi = min(J, j_lo + per);
+    auto entry = [&](long long j) {
+        double dist = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double df = __dsub_rn(xi[k], x1[j * d + k]);
+            dist = __dadd_rn(dist, __dmul_rn(df, df));
+        }
+        return exp((fi + g[j] - dist * inv_median) * inv_eps) * scale * w[j];
+    };
+    double mine = 0.0;
+    for (long long j = j_lo; j < j_hi; ++j) mine += entry(j);
+    seg[threadIdx.x + 1] = mine;
+    if (threadIdx.x == 0) seg[0] = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive prefix of the 256 segment masses, in order; the segment that holds t
+        int p = kSampleThreads - 1;
+        double run = 0.0;
+        for (int q = 0; q < kSampleThreads; ++q) {
+            const double m = seg[q + 1];
+            seg[q] = run;
+            if (run + m > t) {
+                p = q;
+                break;
+            }
+            run += m;
+        }
+        pick = p;
+    }
+    __syncthreads();
+    if (threadIdx.x == pick) {
+        double run = seg[pick];
+        long long last = j_lo < J ? j_lo : J - 1, found = -1;
+        for (long long j = j_lo; j < j_hi; ++j) {
+            const double e = entry(j);
+            if (e > 0.0) last = j;
+            run += e;
+            if (run > t) {
+                found = j;
+                break;
+            }
+        }
+        cols[blockIdx.x] = found >= 0 ? found : last;  // rounding at the very end of a row: its last positive entry
+    }
+}
+
+int coupling_sample(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
+                    const double *f, const double *g, double eps, double out_scale, const double *w, const long long *rows,
+                    const double *targets, int64_t n_samples, long long *cols) {
+    WOTB_REQUIRE(d <= 256, "at most 256 coordinates");
+    if (n_samples > 0)
+        k_coupling_sample<<<(unsigned)n_samples, kSampleThreads, 0, ctx->stream>>>(x0, I, x1, J, d, f, g, 1.0 / median, 1.0 / eps,
+                                                                                   out_scale, w, rows, targets, cols);
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
 }  // namespace wotb

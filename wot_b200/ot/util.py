@@ -128,3 +128,27 @@ def compute_pca(m1, m2, n_components, backend="auto"):
             logging.getLogger("wot").warning("local PCA: rank-deficient input, using scikit-learn (%s)", exc)
             return compute_pca_sklearn(m1, m2, n_components)
         raise
+
+
+def interpolate_with_ot(p0, p1, tmap, interp_frac, size):
+    """Interpolated population of `size` cells between p0 and p1 at fraction `interp_frac`
+    (reference: wot/ot/util.py:109-147): cell pairs (i, j) are drawn with probability
+    tmap_ij / colsum_j^(1 - interp_frac) and mixed as p0[i] (1 - frac) + p1[j] frac.
+
+    `tmap` is a wot_b200.tmap.ImplicitTransportMap (OTModel.compute_implicit_transport_map): the coupling is never
+    materialised, the draw runs on the GPU in float64 (wotb_coupling_sample_host) and consumes the global NumPy
+    random stream exactly like the reference's np.random.choice (one uniform sample per cell), so a seeded
+    reference run and a seeded run of this function pick the same pairs."""
+    from ..tmap import ImplicitTransportMap
+    if not isinstance(tmap, ImplicitTransportMap):
+        raise TypeError("interpolate_with_ot needs an ImplicitTransportMap (OTModel.compute_implicit_transport_map); "
+                        "there is no CPU path")
+    p0 = np.asarray(_dense(p0), dtype=np.float64)
+    p1 = np.asarray(_dense(p1), dtype=np.float64)
+    if p0.shape[1] != p1.shape[1]:
+        raise ValueError("Unable to interpolate. Number of genes do not match")
+    if p0.shape[0] != tmap.shape[0] or p1.shape[0] != tmap.shape[1]:
+        raise ValueError("Unable to interpolate. Tmap size is {}, expected {}".format(tmap.shape, (len(p0), len(p1))))
+    uniforms = np.random.random_sample(size)        # what np.random.choice(..., p=p, size=size) draws internally
+    rows, cols = tmap.sample_pairs(interp_frac, uniforms)
+    return p0[rows] * (1 - interp_frac) + p1[cols] * interp_frac
