@@ -72,7 +72,10 @@ typedef struct wotb_params {
     int32_t kernel; /* enum wotb_kernel */
     int32_t use_graph; /* 1: replay the per-batch launch sequence as a CUDA graph */
     int32_t reserved;  /* flags; bit0 = 1 disables the fused one-sweep iteration kernel (two matvec kernels instead);
-                          bit1 = 1 runs the online kernel on the SIMT FP32 pass instead of the tcgen05 pass */
+                          bit1 = 1 runs the online kernel on the SIMT FP32 pass instead of the tcgen05 pass;
+                          bit2 / bit3 force / forbid the precise 6-segment operands of the tcgen05 pass (default: precise
+                          below a final epsilon of 0.02); bit4 = 1 runs every batch of online iterations as one
+                          persistent cooperative launch */
 } wotb_params;
 
 /* What the reference keeps as locals of the solver; returned for the parity criteria. */

@@ -421,6 +421,23 @@ def test_online_operand_modes_at_defaults(ot, kernel):
     assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
 
 
+@pytest.mark.parametrize("kernel", ["online_fast", "online_precise"])
+def test_persistent_batch_kernel_equals_pass_per_launch(ot, kernel):
+    """k_online_batch (one cooperative launch per batch of iterations, opt-in) computes exactly what the
+    pass-per-launch form computes: same slot-order reductions, same state machine -> bit-identical potentials."""
+    from wot_b200 import synthetic
+    x0, x1, growth = synthetic.day_pair_coords(3300, 3200, d=30, seed=8)      # >= 148 work units in both passes
+    res = {}
+    for batch in (False, True):
+        ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None, G=growth.copy(),
+                                    kernel=kernel, online_batch=batch, want_tmap=False, **DEFAULTS)
+        got = ot.last_solve_info()
+        res[batch] = (np.array(got["f"]), np.array(got["g"]), got["infos"][0]["batches"], got["infos"][0]["launches"])
+    assert res[True][2] == res[False][2]
+    assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][1], res[False][1])
+    assert res[True][3] < res[False][3]          # far fewer launches: the batch kernel really ran
+
+
 def test_atlas_size_pair_vs_oracle(ot):
     """configs[1] at atlas size against the oracle itself (not only size-independent properties): 5000 x 5200 cells,
     growth_iters = 3, default kernel policy; couplings, growth columns, potentials, batch counts."""

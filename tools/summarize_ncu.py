@@ -60,5 +60,27 @@ def full(path):
         print()
 
 
+def traffic(path, key, note=""):
+    """DRAM bytes per launch of the first captured kernel -> profiles/ncu_traffic.json[key] (read by bench.py)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+
+    def val(name):
+        v = float(r[hdr.index(name)].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(name)]]
+    total = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+    dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    rec = json.load(open(dst)) if os.path.exists(dst) else {}
+    rec[key] = {"dram_bytes_per_launch": int(total), "kernel": r[hdr.index("Kernel Name")][:120],
+                "source": "ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), %s%s" % (os.path.basename(path),
+                                                                                               (": " + note) if note else "")}
+    json.dump(rec, open(dst, "w"), indent=1)
+    print(json.dumps(rec[key]))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    cmd = {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]]
+    cmd(*sys.argv[2:])

@@ -131,7 +131,8 @@ def check(rc):
 
 def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tolerance=1e-8, max_iter=1e7,
                 batch_size=5, scaling_iter=3000, extra_iter=1000, inner_iter_max=50, solver=SOLVER_DUALITY_GAP,
-                kernel=KERNEL_STORED, use_graph=True, fuse=True, online_simt=False, online_precise=None, **ignored):
+                kernel=KERNEL_STORED, use_graph=True, fuse=True, online_simt=False, online_precise=None, online_batch=False,
+                **ignored):
     """Pack the ot_config keys the solvers read (ot_model.py:85-87).  Unknown keys are ignored, like the
     reference solvers' **ignored."""
     p = Params()
@@ -146,6 +147,8 @@ def make_params(epsilon=0.05, lambda1=1, lambda2=50, epsilon0=1, tau=10000, tole
     p.reserved = (0 if fuse else 1) | (2 if online_simt else 0)
     if online_precise is not None:
         p.reserved |= 4 if online_precise else 8
+    if online_batch:             # bit4: one persistent cooperative launch per batch of iterations (off by default)
+        p.reserved |= 16
     return p
 
 

@@ -144,6 +144,7 @@ static bool is_pinned(const void *p) {
 template <typename Produce>
 static int stream_coupling_to_host(wotb_ctx *ctx, int64_t I, int64_t J, void *tmap_host, int dtype, double *rowsum_dev,
                                    Produce produce) {
+    NvtxRange range("wotb:coupling -> host");
     const size_t esz = dtype == WOTB_F32 ? 4 : 8;
     const size_t row_bytes = (size_t)J * esz;
     int64_t rows = (int64_t)((size_t)(96u << 20) / row_bytes);
@@ -216,6 +217,9 @@ static int growth_loop(wotb_ctx *ctx, int64_t I, const HostVecs &hv, int growth_
                        wotb_info *infos, Solve solve) {
     WOTB_REQUIRE(growth_iters >= 1, "growth_iters must be >= 1");
     for (int it = 0; it < growth_iters; ++it) {
+        char tag[48];
+        snprintf(tag, sizeof(tag), "wotb:solve growth_iter %d", it);
+        NvtxRange range(tag);
         if (it > 0) WOTB_CUDA(cudaMemcpyAsync(hv.G, hv.rowsum, (size_t)I * 8, cudaMemcpyDeviceToDevice, ctx->stream));
         if (learned_host)
             WOTB_CUDA(cudaMemcpyAsync(learned_host + (size_t)it * I, hv.G, (size_t)I * 8, cudaMemcpyDeviceToHost,
@@ -508,7 +512,10 @@ int wotb_transport_map_from_coords_host(wotb_ctx *ctx, const double *x0_host, in
     WOTB_CUDA(cudaMemcpyAsync(hv.G, G_host, (size_t)I * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (scale_host) WOTB_CUDA(cudaMemcpyAsync(sc, scale_host, (size_t)d * 8, cudaMemcpyHostToDevice, ctx->stream));
     double median = 0.0;
-    WOTB_TRY(cost_median(ctx, x0, I, x1, J, d, scale_host ? sc : nullptr, &median));
+    {
+        NvtxRange range("wotb:cost median (exact select)");
+        WOTB_TRY(cost_median(ctx, x0, I, x1, J, d, scale_host ? sc : nullptr, &median));
+    }
     if (median_out) *median_out = median;
     if (params->kernel == WOTB_KERNEL_STORED) {
         const int64_t ld = round_up(J, 32);

@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/wot_b200.h"
 
 namespace wotb {
@@ -59,6 +61,15 @@ struct PinnedBuf {
     T *as() const {
         return static_cast<T *>(ptr);
     }
+};
+
+// NVTX range for the stages of a transport map (median, cost, solve k, coupling): visible in Nsight Systems / ncu
+// --nvtx, free when no tool is attached (the reference has logger.info lines only).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
 };
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs

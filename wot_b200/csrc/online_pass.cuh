@@ -368,7 +368,10 @@ __global__ void k_online_s0_offsets(SolveVecs V, SolveCtrl *ctrl, double *p0, do
 }
 
 __global__ void k_online_built(SolveCtrl *ctrl) {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && !ctrl->done) ctrl->need_build = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ctrl->grid_bar = 0;  // head of every launch sequence: arrival counter of the persistent batch kernel
+        if (!ctrl->done) ctrl->need_build = 0;
+    }
 }
 
 // raw squared norms in float64 (constant for the solve)

@@ -33,10 +33,11 @@ struct OnlinePasses {
     TcArgs trow, tcol;
     int tgrid_row = 0, tgrid_col = 0;
     bool have_rows = true;
+    bool batch_ok = false;  // the whole batch of iterations runs as one persistent cooperative launch (k_online_batch)
 
     // precise: 6-segment operands (exact accumulation of the large cancelling terms), for small final epsilon
     int setup(wotb_ctx *c, const double *x0_, int64_t I_, const double *x1_, int64_t J_, int d_, bool want_tc, bool precise,
-              int shard, int n_shards, SolveVecs *V, cudaStream_t st) {
+              int shard, int n_shards, SolveVecs *V, cudaStream_t st, bool want_batch = false) {
         ctx = c, x0 = x0_, x1 = x1_, I = I_, J = J_, d = d_;
         tc = want_tc && tc_supported(d);
         ldi = round_up(I, kTcOut), ldj = round_up(J, kTcOut);
@@ -114,6 +115,15 @@ struct OnlinePasses {
             tcol.opA = YA, tcol.opB = XB, tcol.resid = resid_y, tcol.out_n = (int)J, tcol.out_ld = ldj;
             tcol.n_blocks = blocks_j, tcol.out_blk0 = 0, tcol.in_tile0 = t_lo, tcol.in_ntiles = my_tiles;
             tcol.n_stages = plan.n_stages, tcol.part = part, tcol.counters = cnt_j, tcol.dbg = 0, tcol.prof = nullptr;
+            // Optional: one persistent cooperative launch per batch (k_online_batch) when the pair is not sharded and
+            // both passes fill a one-wave grid.  OFF by default: measured on B200 (profiles/r2k) it is 4 % SLOWER than
+            // pass-per-launch with programmatic dependent launch (99.9 vs 96.0 us per iteration at 12.5k x 12.4k) --
+            // the grid barrier + pipeline refill cost what the relaunch costs, and two solves on separate streams can
+            // no longer fill each other's gaps.  WOTB_BATCH=1 or params->reserved bit4 turn it on.
+            const char *nb = getenv("WOTB_BATCH");
+            batch_ok = n_shards == 1 && tgrid_row == ctx->sm_count && tgrid_col == ctx->sm_count &&
+                       (want_batch || (nb && nb[0] == '1')) && tc_batch_configure(plan) == WOTB_OK &&
+                       tc_batch_fits(plan, ctx->sm_count, ctx->sm_count);
         } else {
             XT = (float *)(ob + o_xt), YT = (float *)(ob + o_yt);
             smem = (size_t)3 * kOnChunk * kOnTile * 4;
@@ -171,6 +181,18 @@ struct OnlinePasses {
         k_tc_slots<<<nb, 256, 0, st>>>(V.Qs, (int)J, YA, resid_y, V.Pd, (int)I, XB, plan.kseg, plan.nseg, c, gate);
         return 2;
     }
+    // `n_iters` Sinkhorn iterations (row half-step, column half-step each); returns the number of launches
+    int iterations(cudaStream_t st, const SolveVecs &V, SolveCtrl *c, int n_iters) const {
+        if (batch_ok) {
+            tc_batch_launch(plan, ctx->sm_count, st, trow, tcol, V, c, n_iters);
+            return 1;
+        }
+        for (int s = 0; s < n_iters; ++s) {
+            row_pass(st, V, c, 0, nullptr);
+            col_pass(st, V, c, 0, nullptr);
+        }
+        return 2 * n_iters;
+    }
     void row_pass(cudaStream_t st, const SolveVecs &V, SolveCtrl *c, int mode, double *out) const {
         if (!have_rows) return;
         if (tc)
@@ -221,7 +243,7 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
 
     WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
     OnlinePasses P;
-    WOTB_TRY(P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), online_precise(prm), 0, 1, &V, st));
+    WOTB_TRY(P.setup(ctx, x0, I, x1, J, d, !(prm->reserved & 2), online_precise(prm), 0, 1, &V, st, (prm->reserved & 16) != 0));
     WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     launch_init(ctx, V, d_ctrl, round_up(J, 32));
 
@@ -234,12 +256,9 @@ int sinkhorn_online_impl(wotb_ctx *ctx, const double *x0, int64_t I, const doubl
         if (dg) n += P.s0_pass(st, V, d_ctrl);
         n += P.refresh_slots(st, V, d_ctrl, 1);
         k_online_built<<<1, 32, 0, st>>>(d_ctrl);
-        for (int s = 0; s < slots; ++s) {
-            P.row_pass(st, V, d_ctrl, 0, nullptr);
-            P.col_pass(st, V, d_ctrl, 0, nullptr);
-        }
+        n += P.iterations(st, V, d_ctrl, slots);
         launch_check(ctx, V, d_ctrl, host_done);
-        per_seq = n + 2 + 2 * slots;
+        per_seq = n + 2;
     };
     info->launches = 3;
     {  // count the launches of one sequence without running it twice: the lambda sets per_seq when it runs

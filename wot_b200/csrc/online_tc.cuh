@@ -769,6 +769,285 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     }
 }
 
+// =====================================================================================================================
+// A whole batch of Sinkhorn iterations in ONE persistent cooperative launch: `n_iters` x (row half-step, column
+// half-step), the CTAs meeting at a grid barrier between half-steps.  A pass launched on its own pays ~10 us that are
+// not tile work (measured: 45.2 us at 32.4 units per CTA, 100.4 us at 83.8 units -> 1.07 us per unit + 10.4 us):
+// kernel drain and launch, barrier initialisation, TMEM allocation, pipeline fill.  Here barriers and TMEM are set up
+// once per batch, the ring / accumulator / A-buffer pipelines run through all passes with their phases carried along,
+// and between two passes only the finish chain (last partial -> ticket -> float64 update of the block), the grid
+// barrier and the first B tile's trip from L2 remain.  Everything else -- stream-K dealing, operand layout, epilogue
+// arithmetic, slot-order reductions, the device state machine -- is that of k_online_tc (mode 0).
+// =====================================================================================================================
+__device__ __forceinline__ void tc_grid_barrier(unsigned int *count, unsigned int target) {
+    // called by ONE thread after a CTA-wide barrier; bounded so that a protocol bug traps instead of hanging the GPU
+    __threadfence();
+    atomicAdd(count, 1u);
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int *>(count) < target) {
+        if (++spins > (1u << 28)) __trap();
+    }
+    __threadfence();
+}
+
+template <int KSEG, int EW, int NSEG>
+__global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
+    k_online_batch(TcArgs Arow, TcArgs Acol, SolveVecs V, SolveCtrl *ctrl, int n_iters) {
+    constexpr int RB = kTcRowBlocks, NT = kTcN;
+    constexpr int kEpiThreads = RB * EW * 32;
+    constexpr int NCH = 4 / (EW / 4);
+    constexpr int kseg = KSEG;
+    constexpr int NABUF = NSEG == 3 ? 2 : 1;
+    constexpr uint32_t row_bytes = (uint32_t)kseg * NSEG * 2u;
+    constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ int is_last;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int S = Arow.n_stages;
+    const uint32_t smem0 = smem_u32(tc_smem);
+    const uint32_t bars = smem0;
+    const uint32_t sA = smem0 + kTcTail, sB = sA + NABUF * RB * a_bytes;
+    const uint32_t b_full = bars, b_empty = bars + 8 * kTcMaxStages;
+    const uint32_t b_accf = b_empty + 8 * kTcMaxStages;
+    const uint32_t b_acce = b_accf + 8 * 2 * RB;
+    const uint32_t b_af = b_acce + 8 * 2 * RB, b_ae = b_af + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tc_smem + 8 * (2 * kTcMaxStages + 4 * RB + 4));
+    double *red = reinterpret_cast<double *>(tc_smem) + 32;
+    const int G = gridDim.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            tcb_init(b_full + 8 * s, 1);
+            tcb_init(b_empty + 8 * s, RB);
+        }
+        for (int b = 0; b < 2 * RB; ++b) {
+            tcb_init(b_accf + 8 * b, 1);
+            tcb_init(b_acce + 8 * b, EW);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tcb_init(b_af + 8 * b, 1);
+            tcb_init(b_ae + 8 * b, RB);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (wid == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(kTcTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
+
+    // pipeline positions, carried through all passes of the launch (every role keeps only the ones it uses)
+    int ring = 0;              // B stage the role touches next
+    uint32_t ring_par = 0;     // producer: parity of `empty` it waits for (starts at 1); MMA: parity of `full`
+    uint32_t a_seg = 0;        // out-block segments started so far (A buffer and its parity)
+    uint32_t u = 0;            // work units so far (accumulator buffer and its parity)
+    if (wid == 0) ring_par = 1;
+
+    for (int pass = 0; pass < 2 * n_iters; ++pass) {
+        // every CTA sees the same control state here: it changes only when a column pass closes an iteration, before
+        // the grid barrier.  A finished batch, a tau stop or max_iter end the launch for all of them together.
+        if (!iteration_active(ctrl)) break;
+        const bool col = (pass & 1) != 0;
+        const TcArgs &A = col ? Acol : Arow;
+        const int nt = A.in_ntiles;
+        const long long T = (long long)A.n_blocks * nt;
+        const long long g0 = (long long)blockIdx.x * T / G, g1 = (long long)(blockIdx.x + 1) * T / G;
+        const int b_first = (int)(g0 / nt), t_first = (int)(g0 - (long long)b_first * nt);
+
+        if (wid == 0) {
+            if (lane == 0) {
+                // ===== TMA producer =====  (the offset slots of the B rows were written by other CTAs' generic stores in
+                // the previous pass: ordered by their fence.proxy.async + gpu-scope fence, the grid barrier and this
+                // thread's own fence inside it)
+                const unsigned char *srcA = reinterpret_cast<const unsigned char *>(A.opA);
+                const unsigned char *srcB = reinterpret_cast<const unsigned char *>(A.opB);
+                int b = b_first, t = t_first;
+                for (long long g = g0; g < g1; ++a_seg, ++b, t = 0) {
+                    const int abuf = NABUF == 2 ? (int)(a_seg & 1u) : 0;
+                    const uint32_t a_par = NABUF == 2 ? (a_seg >> 1) & 1u : a_seg & 1u;
+                    tcb_wait(b_ae + 8 * abuf, a_par ^ 1u);
+                    tcb_expect_tx(b_af + 8 * abuf, RB * a_bytes);
+                    const unsigned char *blockA = srcA + (size_t)(A.out_blk0 + b) * (RB * a_bytes);
+                    for (int rb = 0; rb < RB; ++rb)
+                        tcb_bulk_g2s(sA + (abuf * RB + rb) * a_bytes, blockA + (size_t)rb * a_bytes, a_bytes, b_af + 8 * abuf);
+                    const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+                    for (int k = 0; k < n_in_seg; ++k) {
+                        tcb_wait(b_empty + 8 * ring, ring_par);
+                        tcb_expect_tx(b_full + 8 * ring, b_bytes);
+                        tcb_bulk_g2s(sB + (uint32_t)ring * b_bytes, srcB + (size_t)(A.in_tile0 + t + k) * b_bytes, b_bytes,
+                                     b_full + 8 * ring);
+                        if (++ring == S) {
+                            ring = 0;
+                            ring_par ^= 1u;
+                        }
+                    }
+                    g += n_in_seg;
+                }
+            }
+        } else if (wid <= RB) {
+            // ===== MMA issuers, one warp per row block =====
+            constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTcM >> 4) << 24);
+            constexpr uint32_t lbo = 128u, sbo = (uint32_t)kseg * NSEG * 16u;
+            constexpr int ksteps = NSEG * kseg / 16;
+            const int rb = wid - 1;
+            const uint64_t descA0 = umma_desc(sA, lbo, sbo);
+            const uint64_t descB0 = umma_desc(sB, lbo, sbo);
+            int t = t_first;
+            for (long long g = g0; g < g1; ++a_seg, t = 0) {
+                const int abuf = NABUF == 2 ? (int)(a_seg & 1u) : 0;
+                const uint32_t a_par = NABUF == 2 ? (a_seg >> 1) & 1u : a_seg & 1u;
+                tcb_wait(b_af + 8 * abuf, a_par);
+                __syncwarp();
+                const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+                const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
+                for (int k = 0; k < n_in_seg; ++k, ++u) {
+                    const uint32_t buf = u & 1u, par = (u >> 1) & 1u;
+                    tcb_wait(b_acce + 8 * (buf * RB + rb), par ^ 1u);
+                    __syncwarp();
+                    tcb_wait(b_full + 8 * ring, ring_par);
+                    __syncwarp();
+                    tc_fence_after();
+                    const uint64_t descB = descB0 + (uint64_t)(((uint32_t)ring * b_bytes) >> 4);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * kTcAccCols + rb * NT);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < ksteps; ++j)
+                            umma_f16(d_tmem, descA + (uint64_t)(j * 16), descB + (uint64_t)(j * 16), idesc, j > 0 ? 1u : 0u);
+                        tcb_commit(b_accf + 8 * (buf * RB + rb));
+                        tcb_commit(b_empty + 8 * ring);
+                        if (k == n_in_seg - 1) tcb_commit(b_ae + 8 * abuf);
+                    }
+                    __syncwarp();
+                    if (++ring == S) {
+                        ring = 0;
+                        ring_par ^= 1u;
+                    }
+                }
+                g += n_in_seg;
+            }
+        } else if (wid >= kTcEpiWarp0) {
+            // ===== epilogue =====
+            const int ew = wid - kTcEpiWarp0;
+            const int rb = ew / EW, within = ew % EW;
+            const int q = within & 3, h = within >> 2;
+            uint32_t va[32], vb[32];
+            const uint32_t u_end = u + (uint32_t)(g1 - g0);
+            const uint32_t t_buf0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32));
+            const uint32_t accf0 = b_accf + 8 * rb, acce0 = b_acce + 8 * rb;
+            constexpr uint32_t kBufBar = 8 * RB;
+            if (u < u_end) {
+                tcb_wait(accf0 + (u & 1u) * kBufBar, (u >> 1) & 1u);
+                tc_fence_after();
+                WOTB_TMEM_LD32(va, t_buf0 + (u & 1u) * kTcAccCols);
+            }
+            int b = b_first, t = t_first;
+            for (long long g = g0; g < g1; ++b, t = 0) {
+                const int n_in_seg = (int)min((long long)(nt - t), g1 - g);
+                double acc = 0.0;
+                for (int k0 = 0; k0 < n_in_seg; k0 += 8) {
+                    float facc = 0.f;
+                    const int k1 = min(k0 + 8, n_in_seg);
+                    for (int k = k0; k < k1; ++k, ++u) {
+                        const uint32_t buf = u & 1u;
+                        const uint32_t taddr = t_buf0 + buf * kTcAccCols;
+                        float tile_sum = 0.f;
+#pragma unroll
+                        for (int c = 0; c < NCH; c += 2) {
+                            WOTB_TMEM_WAIT32(va);
+                            WOTB_TMEM_LD32(vb, taddr + (c + 1) * 32);
+                            tile_sum += tc_exp2_sum32(va);
+                            WOTB_TMEM_WAIT32(vb);
+                            if (c + 2 < NCH) {
+                                WOTB_TMEM_LD32(va, taddr + (c + 2) * 32);
+                            } else {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) tcb_arrive(acce0 + buf * kBufBar);
+                                if (u + 1 < u_end) {
+                                    const uint32_t nb = buf ^ 1u;
+                                    tcb_wait(accf0 + nb * kBufBar, ((u + 1) >> 1) & 1u);
+                                    tc_fence_after();
+                                    WOTB_TMEM_LD32(va, t_buf0 + nb * kTcAccCols);
+                                }
+                            }
+                            tile_sum += tc_exp2_sum32(vb);
+                        }
+                        facc += tile_sum;
+                    }
+                    acc += (double)facc;
+                }
+                g += n_in_seg;
+                // ---- publish this CTA's share of out block b; the last CTA to arrive finishes the block ----
+                const int blk = A.out_blk0 + b;
+                const long long row = (long long)blk * kTcOut + rb * kTcM + q * 32 + lane;
+                const int c_first = tc_cta_of_unit((long long)b * nt, T, G);
+                const int c_last = tc_cta_of_unit((long long)(b + 1) * nt - 1, T, G);
+                if (EW == 8) {
+                    if (h == 1) red[rb * kTcM + q * 32 + lane] = acc;
+                    named_bar_sync(1, kEpiThreads);
+                    if (h == 0) acc += red[rb * kTcM + q * 32 + lane];
+                }
+                if (h == 0) A.part[(long long)((int)blockIdx.x - c_first) * A.out_ld + row] = acc;
+                __threadfence();
+                named_bar_sync(1, kEpiThreads);
+                if (ew == 0 && lane == 0) {
+                    const unsigned int ticket = atomicAdd(&A.counters[blk], 1u);
+                    is_last = ticket == (unsigned int)(c_last - c_first);
+                }
+                named_bar_sync(1, kEpiThreads);
+                if (is_last) {
+                    __threadfence();
+                    double vmax = 0.0;
+                    if (h == 0) {
+                        if (row < A.out_n) {
+                            double sum = 0.0;
+                            for (int sl = 0; sl <= c_last - c_first; ++sl) sum += __ldcg(A.part + (long long)sl * A.out_ld + row);
+                            sum *= exp2(A.resid[row]);
+                            vmax = col ? online_apply<true>(0, (int)row, sum, V, ctrl, nullptr)
+                                       : online_apply<false>(0, (int)row, sum, V, ctrl, nullptr);
+                            // the offset slots just written are read by other CTAs' TMA loads after the grid barrier
+                            asm volatile("fence.proxy.async.global;" ::: "memory");
+                        }
+                        vmax = warp_max(vmax);
+                        if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+                    }
+                    __threadfence();
+                    named_bar_sync(1, kEpiThreads);
+                    if (ew == 0 && lane == 0) {
+                        A.counters[blk] = 0;
+                        if (col) {
+                            const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
+                            if (ticket == (unsigned int)(A.n_blocks - 1)) {
+                                __threadfence();
+                                ctrl->col_tiles_done = 0;
+                                close_iteration(ctrl);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- end of the half-step: every partial is published, every block finished, the iteration possibly closed ----
+        __syncthreads();
+        // one thread arrives, spins and fences (the gpu-scope fence drops this SM's L1 lines, so the state written by
+        // other CTAs is re-read from L2 by every thread behind the CTA barrier)
+        if (tid == 0) tc_grid_barrier(&ctrl->grid_bar, (unsigned int)(pass + 1) * (unsigned int)G);
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTcTmemCols)
+                     : "memory");
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 inline int tc_kseg(int d) { return (int)round_up(d + 2, 16); }
 inline bool tc_supported(int d) { return tc_kseg(d) <= kTcMaxKseg; }
@@ -855,6 +1134,55 @@ inline void tc_launch_one(const TcPlan &plan, int grid, cudaStream_t st, const T
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr, cfg.numAttrs = tc_use_pdl() ? 1 : 0;
     cudaLaunchKernelEx(&cfg, k_online_tc<COLPASS, K, E, N, P>, A, V, ctrl, mode, rowsum_out);
+}
+
+// ---- the persistent batch kernel: 16 epilogue warps, either operand form ----
+#define WOTB_TC_BATCH_VARIANTS(X) X(16, 3) X(32, 3) X(48, 3) X(16, 6) X(32, 6) X(48, 6)
+
+inline int tc_batch_configure(const TcPlan &plan) {
+    if (plan.ew != 8 || plan.prof) return WOTB_ERR_INVALID;
+    cudaError_t e = cudaErrorInvalidValue;
+#define WOTB_TC_BCFG(K, N)                                                                                                   \
+    if (plan.kseg == K && plan.nseg == N)                                                                                    \
+        e = cudaFuncSetAttribute(k_online_batch<K, 8, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+    WOTB_TC_BATCH_VARIANTS(WOTB_TC_BCFG)
+#undef WOTB_TC_BCFG
+    WOTB_CUDA(e);
+    return WOTB_OK;
+}
+
+// can `grid` CTAs of the batch kernel be co-resident (cooperative launch)?
+inline bool tc_batch_fits(const TcPlan &plan, int grid, int sm_count) {
+    int per_sm = 0;
+    cudaError_t e = cudaErrorInvalidValue;
+#define WOTB_TC_BOCC(K, N)                                                                                                  \
+    if (plan.kseg == K && plan.nseg == N)                                                                                   \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_online_batch<K, 8, N>, plan.threads(), plan.smem);
+    WOTB_TC_BATCH_VARIANTS(WOTB_TC_BOCC)
+#undef WOTB_TC_BOCC
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return per_sm * sm_count >= grid;
+}
+
+inline void tc_batch_launch(const TcPlan &plan, int grid, cudaStream_t st, const TcArgs &Arow, const TcArgs &Acol,
+                            const SolveVecs &V, SolveCtrl *ctrl, int n_iters) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(plan.threads()), cfg.dynamicSmemBytes = plan.smem, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+#define WOTB_TC_BRUN(K, N)                                                                      \
+    if (plan.kseg == K && plan.nseg == N) {                                                     \
+        cudaLaunchKernelEx(&cfg, k_online_batch<K, 8, N>, Arow, Acol, V, ctrl, n_iters);        \
+        return;                                                                                 \
+    }
+    WOTB_TC_BATCH_VARIANTS(WOTB_TC_BRUN)
+#undef WOTB_TC_BRUN
 }
 
 template <bool COLPASS>
@@ -1036,7 +1364,13 @@ __global__ void __launch_bounds__(1024) k_mufu_peak(float *out, int iters) {
     if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
 }
 
-void set_pdl(bool on) { tc_pdl_flag() = on ? 1 : 0; }
+void set_pdl(bool on) {
+    static const bool always = []() {
+        const char *e = getenv("WOTB_PDL_ALWAYS");  // measurement knob: ignore the pipeline's request to turn PDL off
+        return e && e[0] == '1';
+    }();
+    tc_pdl_flag() = (on || always) ? 1 : 0;
+}
 
 int bench_mufu(wotb_ctx *ctx, double *ex2_per_s) {
     WOTB_REQUIRE(ctx && ex2_per_s, "NULL argument");

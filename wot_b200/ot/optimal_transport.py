@@ -183,7 +183,7 @@ def transport_stablev2(C, lambda1, lambda2, epsilon, scaling_iter, G, tau, epsil
 
 
 _SOLVER_IDS = {optimal_transport_duality_gap: _lib.SOLVER_DUALITY_GAP, transport_stablev2: _lib.SOLVER_FIXED_ITERS}
-_EXTRA_KEYS = ("out", "out_dtype", "pinned", "device", "ctx", "use_graph", "fuse")
+_EXTRA_KEYS = ("out", "out_dtype", "pinned", "device", "ctx", "use_graph", "fuse", "online_batch", "want_tmap")
 
 
 def _extras(ignored):

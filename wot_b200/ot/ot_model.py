@@ -319,7 +319,17 @@ class OTModel:
             config["C"] = OTModel.compute_default_cost_matrix(p0_x, p1_x, None if scale is None else np.diag(scale))
         tmap, learned_growth = _ot.compute_transport_matrix(solver=self.solver, **config)
         if ours:
-            final_rows = _ot.last_solve_info()["learned_growth"][-1]
+            last = _ot.last_solve_info()
+            final_rows = last["learned_growth"][-1]
+            if logger.isEnabledFor(logging.INFO):
+                # per-pair metrics: what the reference's progress line lacks
+                iters = sum(i["iters"] for i in last["infos"])
+                ms = sum(i["gpu_ms"] for i in last["infos"])
+                logger.info("tmap {} -> {}: {} x {} cells, {} Sinkhorn iterations in {} solves (final-stage batches {}), "
+                            "{:.1f} ms on the GPU, {:.2f} T kernel entries/s".format(
+                                t0, t1, tmap.shape[0], tmap.shape[1], iters, len(last["infos"]),
+                                [i["batches"][-1] for i in last["infos"]], ms,
+                                2.0 * iters * tmap.shape[0] * tmap.shape[1] / max(ms, 1e-9) / 1e9))
         else:
             final_rows = tmap.sum(axis=1)
         learned_growth = list(learned_growth) + [final_rows]
