@@ -118,6 +118,11 @@ void wotb_set_compute_slots(int32_t n);
  * wot_b200/pipeline.py turns it off while several solves share the GPU (it costs 2 % there). */
 void wotb_set_pdl(int32_t on);
 
+/* Per context: size every persistent / one-wave grid of this context's kernels for n SMs instead of all of them
+ * (n <= 0: all).  Two contexts with complementary limits split the GPU between an HBM-bound stored-K solve and a
+ * MUFU-bound online-K solve of two different day-pairs (wot_b200/pipeline.py, mixed mode). */
+int wotb_set_sm_limit(wotb_ctx *ctx, int32_t n);
+
 /* ---- local PCA: replaces compute_pca, wot/ot/util.py:240-255 -------------------
  * m1 [n1, genes], m2 [n2, genes] float64 row-major (the two days' expression rows, util.py:241-244).
  * Computes what sklearn.decomposition.PCA(k, random_state=58951).fit(x.T) computes with its randomized

@@ -57,6 +57,7 @@ SIGNATURES = {
     "wotb_release_workspace": (None, [_P]),
     "wotb_set_compute_slots": (None, [C.c_int32]),
     "wotb_set_pdl": (None, [C.c_int32]),
+    "wotb_set_sm_limit": (C.c_int, [_P, C.c_int32]),
     "wotb_coupling_apply_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_double, _P, _P, C.c_double,
                                            C.c_double, C.c_int32, _P, C.c_int32, _P]),
     "wotb_coupling_sample_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int32, _P, C.c_double, _P, _P, C.c_double,

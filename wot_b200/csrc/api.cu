@@ -366,6 +366,14 @@ void wotb_set_compute_slots(int32_t n) {
 
 void wotb_set_pdl(int32_t on) { wotb::set_pdl(on != 0); }
 
+int wotb_set_sm_limit(wotb_ctx *ctx, int32_t n) {
+    WOTB_REQUIRE(ctx != nullptr, "ctx is NULL");
+    cudaDeviceProp prop;
+    WOTB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = (n > 0 && n < prop.multiProcessorCount) ? n : prop.multiProcessorCount;
+    return WOTB_OK;
+}
+
 void wotb_release_workspace(wotb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
