@@ -150,6 +150,32 @@ def test_median_is_exact(ot):
         assert np.median(C) == pytest.approx(1.0, abs=1e-15)
 
 
+@pytest.mark.parametrize("shape,ties", [((1100, 1001), "none"), ((1051, 1001), "none"), ((2000, 2100), "none"),
+                                        ((1300, 1200), "some"), ((1200, 1100), "heavy")])
+def test_median_sampled_window_is_exact(shape, ties):
+    """From 2^20 distances on, the median is located by a random sample and found in ONE pass over the distances
+    (count below the window, gather the window, select on the gathered values); it must still be np.median bit for
+    bit: odd and even counts, tie groups inside the window, and data whose ties overflow the window (the device
+    notices and the three-pass radix select takes over)."""
+    import ctypes as C
+    from scipy.spatial.distance import cdist
+    from wot_b200 import _lib
+    n0, n1 = shape
+    rng = np.random.default_rng(n0 + n1)
+    x0, x1 = rng.normal(size=(n0, 30)), rng.normal(size=(n1, 30))
+    if ties == "some":
+        x0[100:400] = x0[0]            # 300 identical cells: every column's distance to them repeats 300 times
+    elif ties == "heavy":
+        x0[:] = x0[rng.integers(0, 3, n0)]      # three distinct cells: each distance value repeats ~400 times
+    want = np.median(cdist(x0, x1, metric="sqeuclidean"))
+    ctx = _lib.context(0)
+    out = np.empty((n0, n1))
+    med = C.c_double()
+    _lib.check(ctx.lib.wotb_default_cost_matrix_host(ctx.handle, _lib.ptr(np.ascontiguousarray(x0)), n0,
+                                                     _lib.ptr(np.ascontiguousarray(x1)), n1, 30, None, _lib.ptr(out), C.byref(med)))
+    assert med.value == want
+
+
 def test_otmodel_default_path_vs_reference(ot, golden):
     """PCA -> cost -> solver -> growth columns (ot_model.py:255-326) against the unmodified reference."""
     from wot_b200 import synthetic
@@ -664,6 +690,44 @@ def test_tiny_and_ragged_shapes_vs_oracle(ot, shape, d, kernel):
     assert_coupling_close(tmap, want)
     got = ot.last_solve_info()
     assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+
+
+@pytest.mark.parametrize("eps", [0.05, 0.01])
+@pytest.mark.parametrize("shape,d", [((1, 1), 3), ((2, 300), 1), ((300, 2), 5), ((257, 129), 14), ((130, 700), 30),
+                                     ((700, 513), 31), ((300, 340), 46)])
+def test_precise_operands_edge_shapes_vs_oracle(ot, shape, d, eps):
+    """The 6-segment operand form over every K-segment width (kseg 16 / 32 / 48: the last one leaves shared memory for
+    ONE B stage), ragged and tiny shapes, at the default epsilon (forced) and at 0.01 (the library's own choice)."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    n0, n1 = shape
+    x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=d, seed=29 + n0 + n1 + d)
+    if n0 * n1 == 1:
+        x1 = x1 + 1.0
+    params = dict(DEFAULTS, epsilon=eps)
+    info = orc.SolveInfo()
+    want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
+                                             gap="marginal", **params)
+    tmap, _ = ot.compute_transport_matrix(ot.optimal_transport_duality_gap, coords=(x0, x1, None), C=None,
+                                          G=growth.copy(), kernel="online_precise" if eps >= 0.02 else "online", **params)
+    assert_coupling_close(tmap, want)
+    got = ot.last_solve_info()
+    _check_potentials(got, info.f, info.g, eps)
+    assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
+
+
+def test_fixed_iters_small_epsilon_online_vs_oracle(ot):
+    """transport_stablev2 (optimal_transport.py:167-236) with a final epsilon of 0.01 on the online kernel: precise
+    operands are chosen from `epsilon` itself for this solver (its schedule ends there, :184-185)."""
+    from oracle import wot_oracle as orc
+    from wot_b200 import synthetic
+    x0, x1, growth = synthetic.day_pair_coords(350, 410, d=30, seed=91)
+    cost = orc.compute_default_cost_matrix(x0, x1)
+    short = dict(DEFAULTS, epsilon=0.01, scaling_iter=400, extra_iter=60, inner_iter_max=50)
+    want = orc.transport_stablev2(C=cost, G=growth, **short)
+    tmap, _ = ot.compute_transport_matrix(ot.transport_stablev2, coords=(x0, x1, None), C=None, G=growth.copy(),
+                                          kernel="online", **short)
+    assert_coupling_close(tmap, want)
 
 
 def test_nan_gap_raises_like_the_reference(ot):

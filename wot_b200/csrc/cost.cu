@@ -260,7 +260,8 @@ __global__ void k_flat_hist(const unsigned long long *__restrict__ buf, const un
     const unsigned long long prefix = st->prefix;
     for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const unsigned long long key = buf[e];
-        if ((key >> (shift + bits)) == prefix) atomicAdd(&hist[(unsigned int)((key >> shift) & ((1u << bits) - 1u))], 1u);
+        const bool in = pass == 0 || (key >> (shift + bits)) == prefix;   // pass 0 has no prefix (and no 64-bit shift)
+        if (in) atomicAdd(&hist[(unsigned int)((key >> shift) & ((1u << bits) - 1u))], 1u);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
@@ -318,6 +319,97 @@ int scale_into(wotb_ctx *ctx, const double *x, int64_t n, int d, const double *s
     return WOTB_OK;
 }
 
+// ---- one-pass median: a sampled window instead of two digit passes -------------------------------------------------
+// The radix select above needs three FP64 passes over all I*J distances (two digits + the gather), 9 ms of a 125 ms
+// atlas step and 0.57 s at 100k x 100k.  Two of them only LOCATE the median; a random sample does that as well:
+// n_s distances of uniformly drawn pairs are selected for the ranks n_s (1/2 -+ delta), delta = 3 / sqrt(n_s) (six
+// standard deviations of a sample quantile), which brackets the true median with probability 1 - 2e-9.  ONE pass
+// over the tiles then counts the distances below the window and gathers the ones inside it (0.1 - 0.6 % of them);
+// the exact order statistics are found on that buffer with the same flat radix select as before.  Every value is
+// still produced by the scipy-ordered float64 arithmetic of dist_tiles, the counts are exact, and the device checks
+// that the wanted ranks really fall inside the gathered window: if not (heavy ties, a bucket larger than the
+// buffer, the one-in-a-billion sample) the three-pass select runs instead.  The result is the exact np.median.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void k_median_sample(const double *__restrict__ x0, long long I, const double *__restrict__ x1, long long J, int d,
+                                unsigned long long *__restrict__ keys, unsigned int n_s) {
+    const unsigned int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_s) return;
+    const unsigned long long h = splitmix64(0x5EEDull + e), h2 = splitmix64(h);
+    const long long i = (long long)__umul64hi(h, (unsigned long long)I), j = (long long)__umul64hi(h2, (unsigned long long)J);
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double df = __dsub_rn(x0[i * d + k], x1[j * d + k]);
+        acc = __dadd_rn(acc, __dmul_rn(df, df));
+    }
+    keys[e] = (unsigned long long)__double_as_longlong(acc);
+}
+
+struct WindowSink {
+    unsigned long long *buf;
+    unsigned int *count;
+    unsigned long long lo, hi;
+    unsigned int cap;
+    unsigned long long below;  // per thread
+    __device__ __forceinline__ void row(long long i, long long j, const double (&v)[4], long long I, long long J) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[c]);
+            const bool valid = i < I && j + c < J;
+            below += (valid && key < lo) ? 1ull : 0ull;
+            const bool in = valid && key >= lo && key <= hi;
+            const unsigned int mask = __ballot_sync(0xffffffffu, in);
+            if (mask) {
+                const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const unsigned int at = base + (unsigned int)__popc(mask & ((1u << lane) - 1u));
+                if (in && at < cap) buf[at] = key;
+            }
+        }
+    }
+};
+
+// st_lo / st_hi: finished flat selects on the sample (their `prefix` is the full key of the window's ends)
+__global__ void __launch_bounds__(kTileThreads) k_median_window(const double *x0, long long I, const double *x1, long long J,
+                                                                int d, const SelectState *st_lo, const SelectState *st_hi,
+                                                                unsigned long long *buf, unsigned int *count, unsigned int cap,
+                                                                unsigned long long *below_total) {
+    WindowSink sink{buf, count, st_lo->prefix, st_hi->prefix, cap, 0ull};
+    dist_tiles(x0, I, x1, J, d, sink);
+    unsigned long long b = sink.below;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(below_total, b);
+}
+
+// Does the window hold the wanted order statistics?  Then the main select continues on the gathered buffer.
+__global__ void k_median_window_check(SelectState *st, const unsigned int *count, unsigned int cap,
+                                      const unsigned long long *below_total, unsigned long long n, int *fallback) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long below = *below_total, c = *count;
+    const unsigned long long target = (n - 1) / 2, upper = n / 2;  // lower and upper middle ranks
+    const bool ok = c <= (unsigned long long)cap && below <= target && upper < below + c;
+    *fallback = ok ? 0 : 1;
+    st->prefix = 0, st->pass = 0, st->n_bucket = 0, st->min_above = ~0ull;
+    for (int b = 0; b < kSelBins; ++b) st->hist[b] = 0;
+    if (ok) {
+        st->use_flat = 1;
+        st->n_less = below;
+        st->rank = target - below;
+    } else {  // the state the three-pass select starts from
+        st->use_flat = 0;
+        st->n_less = 0;
+        st->rank = target;
+    }
+}
+
 int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
                 double *median_host) {
     WOTB_REQUIRE(ctx && x0 && x1 && median_host, "NULL argument");
@@ -325,7 +417,7 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     WOTB_CUDA(cudaSetDevice(ctx->device));
     const double *a, *b;
     WOTB_TRY(scaled_coords(ctx, x0, I, x1, J, d, scale, &a, &b));
-    WOTB_TRY(ctx->select.reserve(sizeof(SelectState)));
+    WOTB_TRY(ctx->select.reserve(3 * sizeof(SelectState)));  // the select itself + the two ends of the sampled window
     SelectState *st = ctx->select.as<SelectState>();
     const unsigned long long n = (unsigned long long)I * (unsigned long long)J;
     SelectState init;
@@ -352,20 +444,71 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
         *out = *pin;
         return WOTB_OK;
     };
-    // always the full cap: a grow-only buffer that never has to be re-allocated mid-run (cudaFree is a device-wide
-    // synchronisation, which would stall the other streams of a pipeline)
-    WOTB_TRY(ctx->part.reserve((size_t)kSelCollectCap * 8 + 256));
+    // ---- sampled window (one pass over the distances) -------------------------------------------------------------
+    unsigned int n_s = 1u << 20;
+    while ((unsigned long long)n_s * 256ull < n && n_s < (1u << 24)) n_s <<= 1;
+    if ((unsigned long long)n_s > n) n_s = 0;                       // tiny problems: the plain select is cheap enough
+    const double delta = n_s ? 3.0 / sqrt((double)n_s) : 0.0;
+    unsigned long long cap64 = (unsigned long long)(2.5 * 2.0 * delta * (double)n) + 65536ull;
+    if (cap64 < kSelCollectCap) cap64 = kSelCollectCap;
+    const bool windowed = shortcut && n_s > 0 && cap64 <= (1ull << 27) && getenv("WOTB_NO_MEDIAN_WINDOW") == nullptr;
+    const unsigned int cap = windowed ? (unsigned int)cap64 : kSelCollectCap;
+    // grow-only buffers that never have to be re-allocated mid-run for pairs of similar size (cudaFree is a
+    // device-wide synchronisation, which would stall the other streams of a pipeline)
+    WOTB_TRY(ctx->part.reserve((size_t)cap * 8 + (size_t)n_s * 8 + 512));
     unsigned long long *buf = ctx->part.as<unsigned long long>() + 32;
     unsigned int *count = ctx->part.as<unsigned int>();
-    WOTB_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
+    unsigned int *count_s = count + 1;
+    unsigned long long *below_total = ctx->part.as<unsigned long long>() + 2;
+    int *fallback_dev = ctx->part.as<int>() + 8;
+    unsigned long long *sample = buf + cap;
+    WOTB_CUDA(cudaMemsetAsync(count, 0, 64, ctx->stream));
     const unsigned int flat_cap = shortcut ? kSelCollectCap : 0u;
+    bool done_by_window = false;
+    if (windowed) {
+        SelectState *st_q[2] = {st + 1, st + 2};
+        k_median_sample<<<(unsigned)cdiv(n_s, 256), 256, 0, ctx->stream>>>(a, I, b, J, d, sample, n_s);
+        WOTB_CUDA(cudaMemcpyAsync(count_s, &n_s, 4, cudaMemcpyHostToDevice, ctx->stream));
+        const double q[2] = {0.5 - delta, 0.5 + delta};
+        for (int w = 0; w < 2; ++w) {
+            SelectState sq;
+            memset(&sq, 0, sizeof(sq));
+            double r = q[w] * (double)n_s;
+            r = r < 0 ? 0 : (r > (double)(n_s - 1) ? (double)(n_s - 1) : r);
+            sq.rank = (unsigned long long)r;
+            sq.min_above = ~0ull;
+            sq.use_flat = 1;
+            WOTB_CUDA(cudaMemcpyAsync(st_q[w], &sq, sizeof(sq), cudaMemcpyHostToDevice, ctx->stream));
+            for (int pass = 0; pass < 6; ++pass) {
+                k_flat_hist<<<592, 256, 0, ctx->stream>>>(sample, count_s, st_q[w]);
+                k_select_pick<<<1, 32, 0, ctx->stream>>>(st_q[w], 0u);
+            }
+        }
+        k_median_window<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st_q[0], st_q[1], buf, count, cap, below_total);
+        k_median_window_check<<<1, 32, 0, ctx->stream>>>(st, count, cap, below_total, n, fallback_dev);
+        for (int pass = 0; pass < 6; ++pass) {      // no-ops on the device (use_flat == 0) when the check failed
+            k_flat_hist<<<592, 256, 0, ctx->stream>>>(buf, count, st);
+            k_select_pick<<<1, 32, 0, ctx->stream>>>(st, 0u);
+        }
+        if (n % 2 == 0) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
+        int *fb_pin = reinterpret_cast<int *>(ctx->status.as<char>() + 192);
+        WOTB_CUDA(cudaMemcpyAsync(fb_pin, fallback_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        Tail t;
+        WOTB_TRY(read_tail(&t));
+        done_by_window = *fb_pin == 0;
+        if (!done_by_window) {  // start the three-pass select from scratch
+            WOTB_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
+            WOTB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    if (!done_by_window)
     for (int pass = 0; pass < 6; ++pass) {
         if (pass == 2) k_select_collect<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st, buf, count, kSelCollectCap);
         if (pass >= 2) k_flat_hist<<<592, 256, 0, ctx->stream>>>(buf, count, st);
         k_select_hist<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
         k_select_pick<<<1, 32, 0, ctx->stream>>>(st, flat_cap);
     }
-    if (n % 2 == 0) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
+    if (n % 2 == 0 && !done_by_window) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
     Tail fin;
     WOTB_TRY(read_tail(&fin));
     double lo, hi;
