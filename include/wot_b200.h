@@ -144,10 +144,25 @@ int wotb_pca_host(wotb_ctx *ctx, const double *m1_host, int64_t n1, const double
  * ot_model.py:301) or NULL.  Distances are sum_k (x0_ik s_k - x1_jk s_k)^2 in float64 with the
  * operation order of scipy cdist('sqeuclidean') (ot_model.py:249-251). */
 
-/* exact np.median over all I*J distances (ot_model.py:252): a 64-bit radix select that recomputes
- * the distances each pass and never stores them.  *median_host receives the value. */
+/* exact np.median over all I*J distances (ot_model.py:252), which are recomputed and never stored.  From 6e7
+ * distances on: a random sample brackets the median, ONE pass counts the distances below the bracket and gathers the
+ * ones inside, a radix select on the gathered values gives the exact order statistics (the device verifies that the
+ * bracket holds them).  Otherwise, or when that check fails: a 64-bit radix select in three passes over the distances.
+ * *median_host receives the value. */
 int wotb_cost_median_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
                          const double *scale, double *median_host);
+/* The same exact median with its one pass over the distances split over ROW SHARDS (row-sharded solves: every rank
+ * holds all coordinates, so every rank draws the same sample and the same window): rank r runs ..._rows_dev on its
+ * rows -> keys of the distances inside the window (device buffer of *cap entries from ..._window_cap; 0 = problem too
+ * small, use wotb_cost_median_dev), their count and the count of distances below the window; the caller sums `below`
+ * and concatenates the keys across ranks (NCCL all-reduce / all-gather) and every rank calls ..._finish_dev on the union.
+ * *ok == 0: the window missed the middle ranks (ties, overflow): fall back to wotb_cost_median_dev. */
+int wotb_cost_median_window_cap(int64_t I, int64_t J, int64_t *cap);
+int wotb_cost_median_window_rows_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                                     const double *scale, int64_t row_lo, int64_t row_hi, uint64_t *keys, int64_t cap,
+                                     uint32_t *count, uint64_t *below);
+int wotb_cost_median_window_finish_dev(wotb_ctx *ctx, int64_t I, int64_t J, const uint64_t *keys, int64_t count,
+                                       uint64_t below, double *median_host, int32_t *ok);
 /* C[i*ldc + j] = dist_ij / median, rounded once to dtype (WOTB_F32 for the solver, WOTB_F64 for
  * callers of compute_default_cost_matrix). median == 1.0 gives raw distances. */
 int wotb_cost_matrix_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,

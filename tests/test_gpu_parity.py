@@ -150,10 +150,10 @@ def test_median_is_exact(ot):
         assert np.median(C) == pytest.approx(1.0, abs=1e-15)
 
 
-@pytest.mark.parametrize("shape,ties", [((1100, 1001), "none"), ((1051, 1001), "none"), ((2000, 2100), "none"),
-                                        ((1300, 1200), "some"), ((1200, 1100), "heavy")])
+@pytest.mark.parametrize("shape,ties", [((8000, 7601), "none"), ((7999, 7601), "none"), ((9000, 8100), "some"),
+                                        ((8200, 7700), "heavy")])
 def test_median_sampled_window_is_exact(shape, ties):
-    """From 2^20 distances on, the median is located by a random sample and found in ONE pass over the distances
+    """From 6e7 distances on, the median is located by a random sample and found in ONE pass over the distances
     (count below the window, gather the window, select on the gathered values); it must still be np.median bit for
     bit: odd and even counts, tie groups inside the window, and data whose ties overflow the window (the device
     notices and the three-pass radix select takes over)."""
@@ -712,7 +712,12 @@ def test_precise_operands_edge_shapes_vs_oracle(ot, shape, d, eps):
                                           G=growth.copy(), kernel="online_precise" if eps >= 0.02 else "online", **params)
     assert_coupling_close(tmap, want)
     got = ot.last_solve_info()
-    _check_potentials(got, info.f, info.g, eps)
+    # The coupling sees f_i + g_j: that sum is held to 1e-4 * eps on every pair.  With a handful of cells a constant may
+    # move between f and g (nearly balanced transport determines it only through the lambda terms): each vector alone
+    # gets twice the allowance here (measured: 1.04e-4 * eps on the 2 x 300, d = 1 case, equal and opposite in f and g).
+    df, dg = got["f"] - info.f, got["g"] - info.g
+    assert np.max(np.abs(df[:, None] + dg[None, :])) <= RTOL * eps
+    assert np.max(np.abs(df)) <= 2 * RTOL * eps and np.max(np.abs(dg)) <= 2 * RTOL * eps
     assert abs(got["infos"][0]["batches"][5] - info.batches[5]) <= 1
 
 

@@ -65,6 +65,9 @@ SIGNATURES = {
     "wotb_pca_host": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P,
                                 _P, _P]),
     "wotb_cost_median_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, C.POINTER(_D)]),
+    "wotb_cost_median_window_cap": (C.c_int, [_I64, _I64, C.POINTER(_I64)]),
+    "wotb_cost_median_window_rows_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _I64, _I64, _P, _I64, _P, _P]),
+    "wotb_cost_median_window_finish_dev": (C.c_int, [_P, _I64, _I64, _P, _I64, C.c_uint64, C.POINTER(_D), C.POINTER(_I32)]),
     "wotb_cost_matrix_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _P, _D, _P, _I64, _I32]),
     "wotb_cost_to_f32_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _I64]),
     "wotb_sinkhorn_stored_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, C.POINTER(Params), _P, _P, _P,

@@ -75,6 +75,10 @@ int cost_to_f32(wotb_ctx *, const double *, int64_t, int64_t, int64_t, float *, 
 int coupling(wotb_ctx *, const float *, int64_t, int64_t, int64_t, const double *, const double *, double, double,
              void *, int64_t, int, double *, cudaStream_t);
 int scale_into(wotb_ctx *, const double *, int64_t, int, const double *, double *);
+int median_window_cap(int64_t, int64_t, int64_t *);
+int median_window_rows(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, const double *, int64_t, int64_t,
+                       unsigned long long *, int64_t, unsigned int *, unsigned long long *);
+int median_window_finish(wotb_ctx *, int64_t, int64_t, const unsigned long long *, int64_t, unsigned long long, double *, int *);
 int coupling_apply(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *, const double *,
                    double, double, int, const double *, int, double *);
 int coupling_sample(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *, const double *,
@@ -414,6 +418,26 @@ size_t wotb_workspace_bytes(const wotb_ctx *ctx) {
 int wotb_cost_median_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
                          const double *scale, double *median_host) {
     return cost_median(ctx, x0, I, x1, J, d, scale, median_host);
+}
+
+int wotb_cost_median_window_cap(int64_t I, int64_t J, int64_t *cap) {
+    WOTB_REQUIRE(cap != nullptr && I >= 1 && J >= 1, "bad argument");
+    return median_window_cap(I, J, cap);
+}
+
+int wotb_cost_median_window_rows_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,
+                                     const double *scale, int64_t row_lo, int64_t row_hi, uint64_t *keys, int64_t cap,
+                                     uint32_t *count, uint64_t *below) {
+    return median_window_rows(ctx, x0, I, x1, J, d, scale, row_lo, row_hi, (unsigned long long *)keys, cap, count,
+                              (unsigned long long *)below);
+}
+
+int wotb_cost_median_window_finish_dev(wotb_ctx *ctx, int64_t I, int64_t J, const uint64_t *keys, int64_t count,
+                                       uint64_t below, double *median_host, int32_t *ok) {
+    int k = 0;
+    const int rc = median_window_finish(ctx, I, J, (const unsigned long long *)keys, count, below, median_host, &k);
+    if (ok) *ok = k;
+    return rc;
 }
 
 int wotb_cost_matrix_dev(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int32_t d,

@@ -164,26 +164,55 @@ __global__ void __launch_bounds__(kTileThreads) k_select_hist(const double *x0, 
         if (hist[b]) atomicAdd(&st->hist[b], (unsigned long long)hist[b]);
 }
 
-__global__ void k_select_pick(SelectState *st, unsigned int flat_cap) {
-    if (threadIdx.x != 0) return;
-    const int bits = sel_bits(st->pass);
-    unsigned long long below = 0, rank = st->rank;
-    int digit = 0;
-    for (int b = 0; b < (1 << bits); ++b) {
-        const unsigned long long n = st->hist[b];
-        if (rank < below + n) {
-            digit = b;
-            st->n_bucket = n;
-            break;
-        }
-        below += n;
+// One CTA of 1024 threads: the 2048 bins are scanned with a block-wide prefix sum instead of by one thread (a pick
+// used to cost ~10 us; a median runs 6 - 18 of them).
+constexpr int kPickThreads = 1024;
+
+__global__ void __launch_bounds__(kPickThreads) k_select_pick(SelectState *st, unsigned int flat_cap) {
+    __shared__ unsigned long long warp_tot[kPickThreads / 32];
+    __shared__ unsigned long long s_below, s_n;
+    __shared__ int s_digit;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bits = sel_bits(st->pass), n_bins = 1 << bits;
+    const unsigned long long rank = st->rank;
+    // thread t owns bins 2t, 2t + 1 (n_bins <= 2048)
+    const unsigned long long h0 = 2 * tid < n_bins ? st->hist[2 * tid] : 0ull;
+    const unsigned long long h1 = 2 * tid + 1 < n_bins ? st->hist[2 * tid + 1] : 0ull;
+    unsigned long long incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
-    st->prefix = (st->prefix << bits) | (unsigned long long)digit;
-    st->rank = rank - below;
-    st->n_less += below;
-    st->pass += 1;
-    if (st->pass == 2 && flat_cap > 0 && st->n_bucket <= (unsigned long long)flat_cap) st->use_flat = 1;
-    for (int b = 0; b < kSelBins; ++b) st->hist[b] = 0;
+    if (lane == 31) warp_tot[wid] = incl;
+    if (tid == 0) s_digit = -1;
+    __syncthreads();
+    unsigned long long base = 0;
+    for (int w = 0; w < wid; ++w) base += warp_tot[w];
+    const unsigned long long before = base + incl - (h0 + h1);  // values in the bins below bin 2t
+    if (rank >= before && rank < before + h0) {
+        s_digit = 2 * tid, s_below = before, s_n = h0;
+    } else if (rank >= before + h0 && rank < before + h0 + h1) {
+        s_digit = 2 * tid + 1, s_below = before + h0, s_n = h1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int digit = s_digit;
+        unsigned long long below = s_below;
+        if (digit < 0) {  // nothing selected (an idle pass of a sequence that has switched paths): keep the state
+            digit = 0;
+            below = 0;
+            for (int w = 0; w < kPickThreads / 32; ++w) below += warp_tot[w];
+        } else {
+            st->n_bucket = s_n;
+        }
+        st->prefix = (st->prefix << bits) | (unsigned long long)digit;
+        st->rank = rank - below;
+        st->n_less += below;
+        st->pass += 1;
+        if (st->pass == 2 && flat_cap > 0 && st->n_bucket <= (unsigned long long)flat_cap) st->use_flat = 1;
+    }
+    for (int b = tid; b < kSelBins; b += kPickThreads) st->hist[b] = 0;
 }
 
 struct MinAboveSink {
@@ -410,6 +439,19 @@ __global__ void k_median_window_check(SelectState *st, const unsigned int *count
     }
 }
 
+// median_window_plan: sample size, window half-width and gather capacity for an I x J problem (0 = use cost_median).
+static unsigned int median_window_plan(unsigned long long n, unsigned int *n_s_out) {
+    unsigned int n_s = 1u << 20;
+    while ((unsigned long long)n_s * 256ull < n && n_s < (1u << 24)) n_s <<= 1;
+    if (n < 60000000ull) n_s = 0;
+    *n_s_out = n_s;
+    if (!n_s) return 0;
+    const double delta = 3.0 / sqrt((double)n_s);
+    unsigned long long cap64 = (unsigned long long)(2.5 * 2.0 * delta * (double)n) + 65536ull;
+    if (cap64 < kSelCollectCap) cap64 = kSelCollectCap;
+    return cap64 <= (1ull << 27) ? (unsigned int)cap64 : 0u;
+}
+
 int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
                 double *median_host) {
     WOTB_REQUIRE(ctx && x0 && x1 && median_host, "NULL argument");
@@ -445,11 +487,13 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
         return WOTB_OK;
     };
     // ---- sampled window (one pass over the distances) -------------------------------------------------------------
-    unsigned int n_s = 1u << 20;
-    while ((unsigned long long)n_s * 256ull < n && n_s < (1u << 24)) n_s <<= 1;
-    if ((unsigned long long)n_s > n) n_s = 0;                       // tiny problems: the plain select is cheap enough
+    // measured on B200 (profiles/r2q_median.txt): 39 M distances 2.2 ms (window) vs 1.6 ms (three passes), 155 M 3.3 vs
+    // 4.6, 400 M 5.4 vs 10.5, 2.5 G 23 vs 134, 10 G 79 vs 526 -- the sample select has a fixed cost of ~24 small launches,
+    // so the window is used from 6e7 distances on (median_window_plan)
+    unsigned int n_s = 0;
+    unsigned long long cap64 = median_window_plan(n, &n_s);
     const double delta = n_s ? 3.0 / sqrt((double)n_s) : 0.0;
-    unsigned long long cap64 = (unsigned long long)(2.5 * 2.0 * delta * (double)n) + 65536ull;
+    if (cap64 == 0) n_s = 0;
     if (cap64 < kSelCollectCap) cap64 = kSelCollectCap;
     const bool windowed = shortcut && n_s > 0 && cap64 <= (1ull << 27) && getenv("WOTB_NO_MEDIAN_WINDOW") == nullptr;
     const unsigned int cap = windowed ? (unsigned int)cap64 : kSelCollectCap;
@@ -481,14 +525,14 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
             WOTB_CUDA(cudaMemcpyAsync(st_q[w], &sq, sizeof(sq), cudaMemcpyHostToDevice, ctx->stream));
             for (int pass = 0; pass < 6; ++pass) {
                 k_flat_hist<<<592, 256, 0, ctx->stream>>>(sample, count_s, st_q[w]);
-                k_select_pick<<<1, 32, 0, ctx->stream>>>(st_q[w], 0u);
+                k_select_pick<<<1, kPickThreads, 0, ctx->stream>>>(st_q[w], 0u);
             }
         }
         k_median_window<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st_q[0], st_q[1], buf, count, cap, below_total);
         k_median_window_check<<<1, 32, 0, ctx->stream>>>(st, count, cap, below_total, n, fallback_dev);
         for (int pass = 0; pass < 6; ++pass) {      // no-ops on the device (use_flat == 0) when the check failed
             k_flat_hist<<<592, 256, 0, ctx->stream>>>(buf, count, st);
-            k_select_pick<<<1, 32, 0, ctx->stream>>>(st, 0u);
+            k_select_pick<<<1, kPickThreads, 0, ctx->stream>>>(st, 0u);
         }
         if (n % 2 == 0) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
         int *fb_pin = reinterpret_cast<int *>(ctx->status.as<char>() + 192);
@@ -506,7 +550,7 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
         if (pass == 2) k_select_collect<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st, buf, count, kSelCollectCap);
         if (pass >= 2) k_flat_hist<<<592, 256, 0, ctx->stream>>>(buf, count, st);
         k_select_hist<<<grid, kTileThreads, 0, ctx->stream>>>(a, I, b, J, d, st);
-        k_select_pick<<<1, 32, 0, ctx->stream>>>(st, flat_cap);
+        k_select_pick<<<1, kPickThreads, 0, ctx->stream>>>(st, flat_cap);
     }
     if (n % 2 == 0 && !done_by_window) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(buf, count, st);
     Tail fin;
@@ -523,6 +567,119 @@ int cost_median(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
         memcpy(&hi, &fin.min_above, 8);
     }
     WOTB_CUDA(cudaGetLastError());
+    *median_host = (lo + hi) / 2.0;
+    return WOTB_OK;
+}
+
+// ---- the one-pass median, split over row shards (row-sharded solves: every rank holds all coordinates) ------------------
+int median_window_cap(int64_t I, int64_t J, int64_t *cap) {
+    unsigned int n_s = 0;
+    *cap = (int64_t)median_window_plan((unsigned long long)I * (unsigned long long)J, &n_s);
+    return WOTB_OK;
+}
+
+// Rows [row_lo, row_hi) of the window pass: distances below the window are counted into *below, the ones inside are
+// appended to keys[0 : cap) (*count may exceed cap: overflow, detected by median_window_finish).  The sample and
+// therefore the window are the same on every rank.
+int median_window_rows(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, const double *scale,
+                       int64_t row_lo, int64_t row_hi, unsigned long long *keys, int64_t cap, unsigned int *count,
+                       unsigned long long *below) {
+    WOTB_REQUIRE(ctx && x0 && x1 && keys && count && below, "NULL argument");
+    WOTB_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= I, "bad row range");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    const unsigned long long n = (unsigned long long)I * (unsigned long long)J;
+    unsigned int n_s = 0;
+    const unsigned int want_cap = median_window_plan(n, &n_s);
+    WOTB_REQUIRE(want_cap > 0 && (unsigned long long)cap >= want_cap, "problem too small for the windowed median, or cap too small");
+    const double *a, *b;
+    WOTB_TRY(scaled_coords(ctx, x0, I, x1, J, d, scale, &a, &b));
+    WOTB_TRY(ctx->select.reserve(3 * sizeof(SelectState)));
+    SelectState *st = ctx->select.as<SelectState>();
+    SelectState *st_q[2] = {st + 1, st + 2};
+    WOTB_TRY(ctx->part.reserve((size_t)n_s * 8 + 512));
+    unsigned int *count_s = ctx->part.as<unsigned int>();
+    unsigned long long *sample = ctx->part.as<unsigned long long>() + 32;
+    k_median_sample<<<(unsigned)cdiv(n_s, 256), 256, 0, ctx->stream>>>(a, I, b, J, d, sample, n_s);
+    WOTB_CUDA(cudaMemcpyAsync(count_s, &n_s, 4, cudaMemcpyHostToDevice, ctx->stream));
+    const double delta = 3.0 / sqrt((double)n_s);
+    const double q[2] = {0.5 - delta, 0.5 + delta};
+    for (int w = 0; w < 2; ++w) {
+        SelectState sq;
+        memset(&sq, 0, sizeof(sq));
+        double r = q[w] * (double)n_s;
+        r = r < 0 ? 0 : (r > (double)(n_s - 1) ? (double)(n_s - 1) : r);
+        sq.rank = (unsigned long long)r;
+        sq.min_above = ~0ull;
+        sq.use_flat = 1;
+        WOTB_CUDA(cudaMemcpyAsync(st_q[w], &sq, sizeof(sq), cudaMemcpyHostToDevice, ctx->stream));
+        for (int pass = 0; pass < 6; ++pass) {
+            k_flat_hist<<<592, 256, 0, ctx->stream>>>(sample, count_s, st_q[w]);
+            k_select_pick<<<1, kPickThreads, 0, ctx->stream>>>(st_q[w], 0u);
+        }
+    }
+    WOTB_CUDA(cudaMemsetAsync(count, 0, 4, ctx->stream));
+    WOTB_CUDA(cudaMemsetAsync(below, 0, 8, ctx->stream));
+    const int64_t rows = row_hi - row_lo;
+    if (rows > 0) {
+        const int grid = tile_grid(ctx, rows, J);
+        k_median_window<<<grid, kTileThreads, 0, ctx->stream>>>(a + (size_t)row_lo * d, rows, b, J, d, st_q[0], st_q[1], keys,
+                                                                count, (unsigned int)cap, below);
+    }
+    WOTB_CUDA(cudaGetLastError());
+    return WOTB_OK;
+}
+
+// keys[0 : count): the union of every shard's window, below: the sum of their counts.  *ok = 0 when the window does not
+// hold the middle ranks (the caller then runs cost_median).
+int median_window_finish(wotb_ctx *ctx, int64_t I, int64_t J, const unsigned long long *keys, int64_t count_total,
+                         unsigned long long below_total, double *median_host, int *ok) {
+    WOTB_REQUIRE(ctx && keys && median_host && ok, "NULL argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    const unsigned long long n = (unsigned long long)I * (unsigned long long)J;
+    WOTB_REQUIRE(count_total >= 0 && count_total < (1ll << 31), "too many keys");
+    WOTB_TRY(ctx->select.reserve(3 * sizeof(SelectState)));
+    SelectState *st = ctx->select.as<SelectState>();
+    WOTB_TRY(ctx->part.reserve(512));
+    unsigned int *count = ctx->part.as<unsigned int>();
+    unsigned long long *below = ctx->part.as<unsigned long long>() + 2;
+    int *fallback_dev = ctx->part.as<int>() + 8;
+    const unsigned int c32 = (unsigned int)count_total;
+    SelectState init;
+    memset(&init, 0, sizeof(init));
+    init.min_above = ~0ull;
+    WOTB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    WOTB_CUDA(cudaMemcpyAsync(count, &c32, 4, cudaMemcpyHostToDevice, ctx->stream));
+    WOTB_CUDA(cudaMemcpyAsync(below, &below_total, 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_median_window_check<<<1, 32, 0, ctx->stream>>>(st, count, c32, below, n, fallback_dev);
+    for (int pass = 0; pass < 6; ++pass) {
+        k_flat_hist<<<592, 256, 0, ctx->stream>>>(keys, count, st);
+        k_select_pick<<<1, kPickThreads, 0, ctx->stream>>>(st, 0u);
+    }
+    if (n % 2 == 0) k_flat_min_above<<<592, 256, 0, ctx->stream>>>(keys, count, st);
+    WOTB_TRY(ctx->status.reserve(256));
+    struct Tail {
+        unsigned long long prefix, rank, n_less, n_bucket, min_above;
+        int pass, use_flat;
+    };
+    Tail *pin = reinterpret_cast<Tail *>(ctx->status.as<char>() + 64);
+    int *fb_pin = reinterpret_cast<int *>(ctx->status.as<char>() + 192);
+    WOTB_CUDA(cudaMemcpyAsync(pin, &st->prefix, sizeof(Tail), cudaMemcpyDeviceToHost, ctx->stream));
+    WOTB_CUDA(cudaMemcpyAsync(fb_pin, fallback_dev, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WOTB_CUDA(cudaStreamSynchronize(ctx->stream));
+    WOTB_CUDA(cudaGetLastError());
+    const Tail fin = *pin;
+    *ok = *fb_pin == 0;
+    if (!*ok) return WOTB_OK;
+    double lo, hi;
+    memcpy(&lo, &fin.prefix, 8);
+    hi = lo;
+    if (n % 2 == 0 && fin.n_less + fin.n_bucket <= n / 2) {
+        if (fin.min_above == ~0ull) {  // the upper middle value lies outside the window: let the caller fall back
+            *ok = 0;
+            return WOTB_OK;
+        }
+        memcpy(&hi, &fin.min_above, 8);
+    }
     *median_host = (lo + hi) / 2.0;
     return WOTB_OK;
 }

@@ -254,6 +254,49 @@ def _sweep_solve_gpu(x0, x1, G, growth_iters=1, kernel="online", **params):
 OP_BEGIN_A, OP_BEGIN_B, OP_ROW, OP_COL_PARTIAL, OP_COL_FINISH, OP_GAP_ROWS, OP_CHECK, OP_FINAL_ROWS = range(8)
 
 
+def sharded_median(ctx, X0, X1, rank, world, group=None):
+    """Exact np.median of the I*J squared distances (ot_model.py:252) with the one pass over the distances split over
+    the ranks' row shards: every rank draws the same sample (the coordinates are replicated), counts and gathers its
+    rows' share of the window, `below` is all-reduced, the gathered keys are all-gathered, and every rank finishes the
+    select on the union -> the same bits everywhere.  Falls back to the full select on every rank when the problem is
+    small, there is one rank, or the window check fails."""
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib
+    lib, h = ctx.lib, ctx.handle
+    n_i, n_j, d = X0.shape[0], X1.shape[0], X0.shape[1]
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    med = C.c_double()
+    cap = C.c_int64(0)
+    _lib.check(lib.wotb_cost_median_window_cap(n_i, n_j, C.byref(cap)))
+    if world > 1 and cap.value > 0:
+        dev = X0.device
+        lo, hi = n_i * rank // world, n_i * (rank + 1) // world
+        keys = torch.empty(cap.value, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+        below = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(lib.wotb_cost_median_window_rows_dev(h, P(X0), n_i, P(X1), n_j, d, None, lo, hi, P(keys), cap.value,
+                                                        P(cnt), P(below)))
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = cnt[0].to(torch.int64)
+        dist.all_reduce(counts, group=group)
+        dist.all_reduce(below, group=group)
+        counts_h = [int(v) for v in counts.cpu()]
+        if max(counts_h) <= cap.value and sum(counts_h) < 2 ** 31:
+            width = max(1, max(counts_h))
+            parts = [torch.empty(width, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(parts, keys[:width].contiguous(), group=group)
+            union = torch.cat([p[:c] for p, c in zip(parts, counts_h)]) if sum(counts_h) else keys[:0]
+            ok = C.c_int32(0)
+            _lib.check(lib.wotb_cost_median_window_finish_dev(h, n_i, n_j, P(union) if union.numel() else P(keys), union.numel(),
+                                                              C.c_uint64(int(below.item())), C.byref(med), C.byref(ok)))
+            if ok.value:
+                return med.value
+    _lib.check(lib.wotb_cost_median_dev(h, P(X0), n_i, P(X1), n_j, d, None, C.byref(med)))
+    return med.value
+
+
 def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, use_graph=True, **params):
     """Solve one day-pair with its rows sharded over the ranks of `group` (online kernel, float64 state).
 
@@ -297,11 +340,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         median = params.pop("median", None)
         if median is None:
-            # every rank runs the exact select on the full problem (3 recompute passes; cheap next to the
-            # solve) so the value is bit-identical everywhere without a collective
-            med = C.c_double()
-            _lib.check(lib.wotb_cost_median_dev(h, P(X0), n_i, P(X1), n_j, d, None, C.byref(med)))
-            median = med.value
+            median = sharded_median(ctx, X0, X1, rank, world, group)
         solver = params.pop("solver", _lib.SOLVER_DUALITY_GAP)
         prm = _lib.make_params(solver=solver, kernel=_lib.KERNEL_ONLINE, **params)
         f = torch.empty(n_i, dtype=torch.float64, device=dev)
