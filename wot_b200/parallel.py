@@ -339,8 +339,14 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         n_i, n_j, d = X0.shape[0], X1.shape[0], X0.shape[1]
         P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         median = params.pop("median", None)
+        median_ms = 0.0
         if median is None:
+            mev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            mev[0].record(stream)
             median = sharded_median(ctx, X0, X1, rank, world, group)
+            mev[1].record(stream)
+            mev[1].synchronize()
+            median_ms = mev[0].elapsed_time(mev[1])
         solver = params.pop("solver", _lib.SOLVER_DUALITY_GAP)
         prm = _lib.make_params(solver=solver, kernel=_lib.KERNEL_ONLINE, **params)
         f = torch.empty(n_i, dtype=torch.float64, device=dev)
@@ -422,6 +428,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
             lib.wotb_online_close(solve)
         out_info = info.as_dict()
         out_info["gpu_ms"] = ev[0].elapsed_time(ev[1])
+        out_info["median_ms"] = median_ms
     return {"f": f, "g": g, "rowsum": rowsum, "rows": (lo.value, hi.value), "median": median, "info": out_info,
             "ctx": ctx, "coords": (X0, X1), "stream": stream}
 
