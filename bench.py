@@ -477,20 +477,30 @@ def e2e_api_block(local_rank, n_pairs, scale):
 
 
 def row_sharded_block(torch, dist, rank, world, local_rank, mufu_peak, n=100000):
-    """BASELINE.json configs[3]: ONE 100k x 100k pair (seed 3), online kernel, rows sharded over the ranks, an NCCL
-    all-reduce per Sinkhorn iteration.  Parity: the same solve on one GPU (every rank runs it redundantly), float64
+    """BASELINE.json configs[3]: ONE 100k x 100k pair (seed 3), online kernel, rows sharded over the ranks; per Sinkhorn
+    iteration the ranks exchange over peer memory from inside the pass kernels (headline) or with one NCCL all-reduce
+    (`nccl_exchange`, timed beside it).  Parity: the same solve on one GPU (every rank runs it redundantly), float64
     blockwise marginals of the returned potentials on sampled rows, the fixed-point equations."""
     from wot_b200 import _lib, parallel, synthetic
     x0, x1, growth = synthetic.day_pair_coords(n, n, d=D, seed=3)
     dev = torch.device("cuda", local_rank)
-    res = parallel.sharded_online_solve(x0, x1, growth, **DEFAULTS)      # warm-up: workspaces, NCCL channels
-    timers = {}
-    res = parallel.sharded_online_solve(x0, x1, growth, timers=timers, **DEFAULTS)
+    def timed(exchange, median=None):
+        kw = dict(DEFAULTS, exchange=exchange)
+        if median is not None:
+            kw["median"] = median
+        parallel.sharded_online_solve(x0, x1, growth, **kw)               # warm-up: workspaces, NCCL channels, mappings
+        tm = {}
+        r = parallel.sharded_online_solve(x0, x1, growth, timers=tm, **kw)
+        t = torch.tensor([r["info"]["gpu_ms"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return r, tm, float(t.item())
+
+    # the NCCL exchange (one all-reduce per iteration inside the graph), then the peer-memory exchange (no collective:
+    # NVLink stores from the passes' finishing code); the block's headline is the one `exchange="auto"` selects
+    res_n, timers_n, ms_nccl = timed("nccl")
+    res, timers, solve_ms = timed("auto", median=res_n["median"])
     info = res["info"]
-    solve_ms = info["gpu_ms"]
-    t = torch.tensor([solve_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    solve_ms = float(t.item())
+    info["median_ms"] = res_n["info"].get("median_ms")
     f, g, rowsum = res["f"], res["g"], res["rowsum"]
     # ---- the same pair on ONE GPU (redundantly on every rank): batch counts must be identical ----
     ctx = res["ctx"]
@@ -531,8 +541,14 @@ def row_sharded_block(torch, dist, rank, world, local_rank, mufu_peak, n=100000)
            "median_ms": info.get("median_ms"), "median_note": "exact np.median of the 1e10 distances, one pass split over the "
                                                               "ranks' row shards (counts all-reduced, window keys all-gathered)",
            "iters_per_s": iters / sec, "mufu_frac_aggregate": 2.0 * n * n * iters / sec / 1e12 / (world * mufu_peak),
-           "allreduce_us_per_iter": timers.get("allreduce_us_per_iter"), "allreduce_bytes": timers.get("allreduce_bytes"),
-           "launch_mode": timers.get("mode"),
+           "exchange": timers.get("exchange"), "launch_mode": timers.get("mode"),
+           "peer_bytes_out_per_iter": timers.get("peer_bytes_out_per_iter"),
+           "nccl_exchange": {"solve_ms": ms_nccl, "iters": res_n["info"]["iters"], "batches": res_n["info"]["batches"],
+                             "iters_per_s": res_n["info"]["iters"] / (ms_nccl * 1e-3),
+                             "mufu_frac_aggregate": 2.0 * n * n * res_n["info"]["iters"] / (ms_nccl * 1e-3) / 1e12 / (world * mufu_peak),
+                             "allreduce_us_per_iter": timers_n.get("allreduce_us_per_iter"),
+                             "allreduce_bytes": timers_n.get("allreduce_bytes"), "launch_mode": timers_n.get("mode"),
+                             "max_abs_df_over_eps_vs_headline": float(torch.abs(res_n["f"] - f).max().item() / info["eps_final"])},
            "one_gpu": {"iters": one["iters"], "batches": one["batches"], "solve_ms": one["gpu_ms"]},
            "speedup_vs_one_gpu": one["gpu_ms"] / solve_ms, "efficiency_vs_one_gpu": one["gpu_ms"] / solve_ms / world,
            "parity": {"batches_equal_one_gpu": info["batches"] == one["batches"], "iters_equal_one_gpu": iters == one["iters"],

@@ -248,6 +248,30 @@ int wotb_online_state(void *solve, wotb_info *info, int32_t *done);
 int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi);
 void wotb_online_close(void *solve);
 
+/* ---- the same solve exchanging over PEER MEMORY (NVLink / NVSwitch) instead of the caller's all-reduce ---------
+ * The per-iteration exchange of the row-sharded solve (the reference has no counterpart: optimal_transport.py:133-134
+ * run on one host) moves into the kernels: the finishing code of the row half-step stores (a_i, row sum) of the
+ * rank's rows into EVERY rank's exchange buffer while the pass is still running, the column pass does the same with
+ * its partial column sums, one warp exchanges flags and one kernel adds the partial sums in rank order (identical bits
+ * on every rank) and applies the b update.  No collective library call, no `exchange` traffic between the steps:
+ *
+ *   once:           wotb_online_open; wotb_online_peer_bytes; wotb_peer_alloc (own buffer + 64-byte IPC handle);
+ *                   exchange the handles (any host transport); wotb_peer_open for every other rank;
+ *                   wotb_online_attach_peers; a host barrier over all ranks
+ *   per batch:      step BEGIN_A, step BEGIN_B            (no all-reduce)
+ *   per iteration:  step ROW, step COL_PARTIAL, step COL_FINISH   (no all-reduce)
+ *   per batch end:  step CHECK, wotb_online_state
+ *   when done:      step FINAL_ROWS  -> exchange[0:I] holds the coupling's row sums on every rank
+ *
+ * A rank whose peers never arrive traps after 20 s instead of hanging.  Up to 8 ranks.  Ranks inside one process may
+ * pass plain device pointers to wotb_online_attach_peers instead of IPC mappings. */
+int wotb_peer_alloc(wotb_ctx *ctx, int64_t bytes, void **ptr, void *ipc_handle_64 /* may be NULL */);
+int wotb_peer_open(wotb_ctx *ctx, const void *ipc_handle_64, void **ptr);
+int wotb_peer_close(wotb_ctx *ctx, void *ptr);   /* a mapping obtained from wotb_peer_open */
+int wotb_peer_free(wotb_ctx *ctx, void *ptr);    /* a buffer obtained from wotb_peer_alloc */
+int wotb_online_peer_bytes(void *solve, int32_t world, int64_t *bytes);
+int wotb_online_attach_peers(void *solve, int32_t world, void *const *bufs /* [world], own buffer at [shard] */);
+
 /* ---- a coupling applied to populations without materialising it ------------------
  * Replaces the products of TransportMapModel.push_forward / pull_back, wot/tmap/transport_map_model.py:290
  * (p @ tmap.X) and :356 (tmap.X @ p.T), where p stacks ALL populations (np.vstack, :285, :351): the coupling of a

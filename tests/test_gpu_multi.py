@@ -18,6 +18,34 @@ def test_stepping_path_single_gpu(eps):
     assert "OK" in out.stdout
 
 
+@pytest.mark.parametrize("world,eps", [(2, "0.05"), (3, "0.05"), (2, "0.01")])
+def test_peer_memory_exchange_in_process_ranks(world, eps):
+    """The peer-memory exchange (stores from the passes' finishing code into every rank's buffer, flag barrier,
+    rank-ordered sums; no collective) with the ranks as threads of one process on ONE GPU: oracle parity, identical
+    bits on every rank, identical batch counts to the one-rank solve."""
+    # streams of one process can share a hardware work queue: a rank's kernels must never queue up behind a kernel of
+    # ANOTHER rank that waits for this rank's flag, so the host waits for every flag kernel (online_solve.cuh)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", WOTB_PEER_HOST_SYNC="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_sharded_threads.py"), "1500", "1637",
+                          str(world), eps], capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "ALL OK" in out.stdout
+
+
+@pytest.mark.parametrize("eps", ["0.05", "0.01"])
+def test_row_sharded_two_gpus_peer_memory(eps):
+    """The same exchange between two processes / two GPUs (cudaIpc mappings, NVLink stores), CUDA graph per batch."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29536" if eps == "0.05" else "29537",
+           os.path.join(ROOT, "tests", "run_sharded_pair.py"), "3000", "3301", eps, "peer"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("OK") == 2
+
+
 @pytest.mark.parametrize("eps", ["0.05", "0.01"])
 def test_row_sharded_two_gpus_nccl(eps):
     import torch
@@ -25,7 +53,7 @@ def test_row_sharded_two_gpus_nccl(eps):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29533" if eps == "0.05" else "29534",
-           os.path.join(ROOT, "tests", "run_sharded_pair.py"), "3000", "3301", eps]
+           os.path.join(ROOT, "tests", "run_sharded_pair.py"), "3000", "3301", eps, "nccl"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("OK") == 2

@@ -87,6 +87,12 @@ SIGNATURES = {
     "wotb_online_state": (C.c_int, [_P, C.POINTER(Info), C.POINTER(_I32)]),
     "wotb_online_rows": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "wotb_online_close": (None, [_P]),
+    "wotb_peer_alloc": (C.c_int, [_P, _I64, C.POINTER(_P), _P]),
+    "wotb_peer_open": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "wotb_peer_close": (C.c_int, [_P, _P]),
+    "wotb_peer_free": (C.c_int, [_P, _P]),
+    "wotb_online_peer_bytes": (C.c_int, [_P, _I32, C.POINTER(_I64)]),
+    "wotb_online_attach_peers": (C.c_int, [_P, _I32, C.POINTER(_P)]),
     "wotb_bench_matvec_dev": (C.c_int, [_P, _I64, _I64, _I32, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]),
     "wotb_online_rowsums_dev": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _D, _P, _P, _I32, _I32, _P, C.POINTER(_D)]),
     "wotb_bench_mufu_dev": (C.c_int, [_P, C.POINTER(_D)]),

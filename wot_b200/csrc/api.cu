@@ -91,6 +91,8 @@ int online_step(OnlineSolve *, int, double *);
 int online_state(OnlineSolve *, wotb_info *, int *);
 void online_rows(OnlineSolve *, int64_t *, int64_t *);
 void online_close(OnlineSolve *);
+int64_t online_peer_bytes_of(OnlineSolve *, int);
+int online_attach(OnlineSolve *, int, void *const *);
 int sinkhorn_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const wotb_params *, double *, double *, double *, wotb_info *);
 int online_rowsums(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
@@ -642,6 +644,60 @@ int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi) {
 }
 
 void wotb_online_close(void *solve) { online_close((OnlineSolve *)solve); }
+
+// ---- peer-memory exchange of the row-sharded solve -------------------------------------------------------------
+int wotb_peer_alloc(wotb_ctx *ctx, int64_t bytes, void **ptr, void *ipc_handle_64) {
+    WOTB_REQUIRE(ctx && ptr && bytes > 0, "bad argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    WOTB_CUDA(cudaMalloc(&p, (size_t)bytes));
+    cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+    if (e == cudaSuccess && ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, p);
+        if (e == cudaSuccess) memcpy(ipc_handle_64, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        WOTB_CUDA(e);
+    }
+    *ptr = p;
+    return WOTB_OK;
+}
+
+int wotb_peer_open(wotb_ctx *ctx, const void *ipc_handle_64, void **ptr) {
+    WOTB_REQUIRE(ctx && ipc_handle_64 && ptr, "NULL argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle_64, sizeof(h));
+    WOTB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return WOTB_OK;
+}
+
+int wotb_peer_close(wotb_ctx *ctx, void *ptr) {
+    WOTB_REQUIRE(ctx && ptr, "NULL argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    WOTB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return WOTB_OK;
+}
+
+int wotb_peer_free(wotb_ctx *ctx, void *ptr) {
+    WOTB_REQUIRE(ctx && ptr, "NULL argument");
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    WOTB_CUDA(cudaFree(ptr));
+    return WOTB_OK;
+}
+
+int wotb_online_peer_bytes(void *solve, int32_t world, int64_t *bytes) {
+    WOTB_REQUIRE(solve && bytes && world >= 1, "bad argument");
+    *bytes = online_peer_bytes_of((OnlineSolve *)solve, world);
+    return WOTB_OK;
+}
+
+int wotb_online_attach_peers(void *solve, int32_t world, void *const *bufs) {
+    return online_attach((OnlineSolve *)solve, world, bufs);
+}
 
 int wotb_bench_matvec_dev(wotb_ctx *ctx, int64_t I, int64_t J, int32_t reps, double *ms_row, double *ms_col,
                           double *ms_fused) {

@@ -146,6 +146,21 @@ __device__ __forceinline__ void tc_store_in_offset(__half *opB, long long idx, d
     }
 }
 
+// ---- row-sharded solves over peer memory (PeerX, solver_state.cuh): the finishing code of a pass stores its results
+// into every rank's exchange buffer (own included) while the rest of the pass is still running; the stores cross
+// NVLink as they are issued, and the kernel boundary in front of k_peer_barrier makes them visible system-wide.
+__device__ __forceinline__ void peer_store_row(const PeerX &X, int o, double a, double s) {
+    const int p = (int)(X.seq & 1ull);
+    for (int w = 0; w < X.world; ++w) {
+        reinterpret_cast<double *>(X.buf[w] + X.off_a[p])[o] = a;
+        reinterpret_cast<double *>(X.buf[w] + X.off_s[p])[o] = s;
+    }
+}
+__device__ __forceinline__ void peer_store_col_partial(const PeerX &X, int o, double s) {
+    const int p = (int)(X.seq & 1ull);
+    for (int w = 0; w < X.world; ++w) reinterpret_cast<double *>(X.buf[w] + X.off_t[p])[(long long)X.rank * X.ld_t + o] = s;
+}
+
 // What a finished out entry does with its reduced sum s (shared by the SIMT and the tcgen05 pass kernels).
 // Returns |a| or |b| for the tau test of a half-step, 0 otherwise.
 template <bool COLPASS>
@@ -162,6 +177,7 @@ __device__ __forceinline__ double online_apply(int mode, int o, double s, const 
             if (ctrl->batch_done == 0) V.sfirst[o] = s;
             V.Pd[o] = (ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
             if (V.tcXB) tc_store_in_offset(V.tcXB, o, V.Pd[o], V.tc_kseg, V.tc_nseg);
+            if (V.peer) peer_store_row(*V.peer, o, a, s);
             vmax = fabs(a);
         } else {
             const double b = scaling_update(ctrl->lq, s, ctrl->alpha2, V.lv[o]);
@@ -177,6 +193,8 @@ __device__ __forceinline__ double online_apply(int mode, int o, double s, const 
         rowsum_out[o] = V.a[cur][o] * s * (ctrl->out_scale * (double)J);
     } else if (mode == 3) {
         V.sumK0_part[o] = s;
+    } else if (COLPASS && V.peer) {
+        peer_store_col_partial(*V.peer, o, s);
     } else {
         rowsum_out[o] = s;
     }

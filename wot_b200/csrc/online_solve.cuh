@@ -372,6 +372,128 @@ __global__ void k_online_col_finish(SolveVecs V, SolveCtrl *ctrl, const double *
     }
 }
 
+// =================================================================================================
+// The same solve exchanging over PEER MEMORY instead of NCCL (PeerX in solver_state.cuh).
+//
+// Per iteration: the row half-step's finishing code stores (a_i, s_i) of the rank's own rows into every rank's
+// exchange buffer, the column pass's finishing code stores the rank's partial column sums likewise -- the transfer
+// rides on the passes, 256 rows at a time, instead of following them; then ONE warp exchanges flags (k_peer_barrier)
+// and k_peer_finish takes the gathered a, adds the `world` partial sums of every column in rank order and applies the b
+// update.  Three launches per iteration, none of them a library collective; no export / import staging, no memset.
+// The S0 partials of the final stage and the coupling row sums at the end are gathers of row slices through the
+// same buffers (k_peer_push_slice / k_peer_import_vec).
+// =================================================================================================
+__device__ __forceinline__ bool peer_gate(const SolveCtrl *c, int gate) {
+    // 0: a Sinkhorn iteration is due; 3: the S0 pass of the final duality-gap stage is due; -1: always
+    if (gate == 0) return iteration_active(c);
+    if (gate == 3)
+        return !(c->done || !c->need_build || c->solver != WOTB_SOLVER_DUALITY_GAP || c->stage != WOTB_N_STAGES - 1);
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long peer_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// One warp: lane w tells rank w that everything this rank stored for exchange `seq` has landed (the stores were issued
+// by kernels that completed before this one started), then waits for rank w's flag.  Bounded: a peer that never
+// arrives (crashed process, diverged control flow) traps this context after kPeerTimeoutNs instead of hanging the GPU.
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+__global__ void k_peer_barrier(PeerX *X, const SolveCtrl *ctrl, int gate) {
+    if (!peer_gate(ctrl, gate)) return;
+    const int w = threadIdx.x;
+    if (w >= X->world) return;
+    const unsigned long long seq = X->seq, val = seq + 1;
+    const int p = (int)(seq & 1ull);
+    __threadfence_system();
+    unsigned long long *remote = reinterpret_cast<unsigned long long *>(X->buf[w] + X->off_flags) + p * kMaxPeers + X->rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(val) : "memory");
+    const unsigned long long *mine =
+        reinterpret_cast<const unsigned long long *>(X->buf[X->rank] + X->off_flags) + p * kMaxPeers + w;
+    const unsigned long long t0 = peer_timer_ns();
+    unsigned long long got;
+    unsigned int spins = 0;
+    do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(mine) : "memory");
+        if (got < val && (++spins & 1023u) == 0 && peer_timer_ns() - t0 > kPeerTimeoutNs) __trap();
+    } while (got < val);
+    __threadfence_system();
+}
+
+// own slice [lo, hi) of a row vector into region a of every rank's buffer
+__global__ void k_peer_push_slice(const double *__restrict__ src, int lo, int hi, PeerX *X, const SolveCtrl *ctrl, int gate) {
+    if (!peer_gate(ctrl, gate)) return;
+    const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    const int p = (int)(X->seq & 1ull);
+    const double v = src[i];
+    for (int w = 0; w < X->world; ++w) reinterpret_cast<double *>(X->buf[w] + X->off_a[p])[i] = v;
+}
+
+// gathered row vector out of the own buffer (after k_peer_barrier); the last block closes the exchange
+__global__ void k_peer_import_vec(PeerX *X, const SolveCtrl *ctrl, double *__restrict__ dst, int n, int gate) {
+    if (!peer_gate(ctrl, gate)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (int)(X->seq & 1ull);
+    if (i < n) dst[i] = reinterpret_cast<const double *>(X->buf[X->rank] + X->off_a[p])[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&X->ticket, 1u) == gridDim.x - 1) {
+            X->ticket = 0;
+            __threadfence();
+            X->seq += 1;
+        }
+    }
+}
+
+// after k_peer_barrier: the gathered a (k_import_a) and the reduced column sums with the b update
+// (k_online_col_finish) in one launch over max(I, J) entries
+__global__ void k_peer_finish(SolveVecs V, SolveCtrl *ctrl, PeerX *X) {
+    if (!iteration_active(ctrl)) return;
+    const int I = ctrl->I, J = ctrl->J, cur = ctrl->cur;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (int)(X->seq & 1ull);
+    const unsigned char *mine = X->buf[X->rank];
+    double vmax = 0.0;
+    if (idx < I) {
+        const double a = reinterpret_cast<const double *>(mine + X->off_a[p])[idx];
+        const double s = reinterpret_cast<const double *>(mine + X->off_s[p])[idx];
+        V.a[cur ^ 1][idx] = a;
+        V.s[idx] = s;
+        if (ctrl->batch_done == 0) V.sfirst[idx] = s;
+        V.Pd[idx] = (ctrl->c1 * V.u[idx] - ctrl->c2 * V.nx[idx] + log2(a) - log2((double)I));
+        if (V.tcXB) tc_store_in_offset(V.tcXB, idx, V.Pd[idx], V.tc_kseg, V.tc_nseg);
+        vmax = fabs(a);
+    }
+    if (idx < J) {
+        const double *tp = reinterpret_cast<const double *>(mine + X->off_t[p]) + idx;
+        double t = 0.0;
+        for (int w = 0; w < X->world; ++w) t += tp[(long long)w * X->ld_t];  // rank order: the same bits on every rank
+        const double b = scaling_update(ctrl->lq, t, ctrl->alpha2, V.lv[idx]);
+        V.b[cur ^ 1][idx] = b;
+        V.t[idx] = t;
+        V.Qd[idx] = (ctrl->c1 * V.v[idx] - ctrl->c2 * V.ny[idx] + log2(b) - log2((double)J));
+        if (V.tcYB) tc_store_in_offset(V.tcYB, idx, V.Qd[idx], V.tc_kseg, V.tc_nseg);
+        vmax = fmax(vmax, fabs(b));
+    }
+    vmax = warp_max(vmax);
+    if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            ctrl->col_tiles_done = 0;
+            X->seq += 1;
+            close_iteration(ctrl);
+        }
+    }
+}
+
 struct OnlineSolve {
     wotb_ctx *ctx;
     int64_t I, J;
@@ -380,7 +502,55 @@ struct OnlineSolve {
     SolveCtrl h;
     OnlinePasses P;
     int64_t launches;
+    int shard = 0;
+    bool peer_host_sync = false;  // WOTB_PEER_HOST_SYNC=1: see peer_barrier()
+    PeerX *d_peer = nullptr;  // device copy of the peer table when the solve exchanges over peer memory (cudaMalloc)
+    int world = 1;
 };
+
+inline size_t peer_align(size_t b) { return (b + 255) / 256 * 256; }
+
+// bytes of one rank's exchange buffer for an I x J solve on `world` ranks
+size_t online_peer_bytes(int64_t I, int64_t J, int world) {
+    const size_t ld_t = peer_align((size_t)J * 8) / 8;
+    return 256 + 2 * (2 * peer_align((size_t)I * 8) + peer_align((size_t)world * ld_t * 8));
+}
+
+// bufs[w]: rank w's exchange buffer as mapped into THIS process (own buffer at [shard]).  Zeroes the own flags; the
+// caller must put a barrier over all ranks between this call and the first step.
+int online_attach_peers(OnlineSolve *S, int world, void *const *bufs) {
+    WOTB_REQUIRE(S && bufs, "NULL argument");
+    WOTB_REQUIRE(world >= 1 && world <= kMaxPeers, "peer exchange supports 1..8 ranks");
+    wotb_ctx *ctx = S->ctx;
+    WOTB_CUDA(cudaSetDevice(ctx->device));
+    PeerX h;
+    memset(&h, 0, sizeof(h));
+    h.rank = S->shard, h.world = world;
+    for (int w = 0; w < world; ++w) {
+        WOTB_REQUIRE(bufs[w] != nullptr, "peer buffer is NULL");
+        h.buf[w] = static_cast<unsigned char *>(bufs[w]);
+    }
+    const size_t dI = peer_align((size_t)S->I * 8);
+    h.ld_t = (long long)(peer_align((size_t)S->J * 8) / 8);
+    const size_t dT = peer_align((size_t)world * h.ld_t * 8);
+    size_t off = 256;
+    h.off_flags = 0;
+    for (int p = 0; p < 2; ++p) {
+        h.off_a[p] = (long long)off, off += dI;
+        h.off_s[p] = (long long)off, off += dI;
+        h.off_t[p] = (long long)off, off += dT;
+    }
+    if (!S->d_peer) WOTB_CUDA(cudaMalloc(&S->d_peer, sizeof(PeerX)));
+    cudaStream_t st = ctx->stream;
+    WOTB_CUDA(cudaMemcpyAsync(S->d_peer, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    WOTB_CUDA(cudaMemsetAsync(h.buf[h.rank], 0, 256, st));
+    WOTB_CUDA(cudaStreamSynchronize(st));
+    S->V.peer = S->d_peer;
+    S->world = world;
+    const char *hs = getenv("WOTB_PEER_HOST_SYNC");
+    S->peer_host_sync = hs && hs[0] == '1';
+    return WOTB_OK;
+}
 
 int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, int64_t J, int d, double median,
                 const double *G, const wotb_params *prm, int shard, int n_shards, double *f, double *g,
@@ -389,7 +559,7 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     WOTB_REQUIRE(d >= 1 && median > 0, "d must be >= 1 and the median positive");
     WOTB_REQUIRE(n_shards >= 1 && shard >= 0 && shard < n_shards, "bad shard index");
     OnlineSolve *S = new OnlineSolve();
-    S->ctx = ctx, S->I = I, S->J = J, S->launches = 0;
+    S->ctx = ctx, S->I = I, S->J = J, S->launches = 0, S->shard = shard;
     int rc = init_ctrl(prm, I, J, &S->h, median);
     if (rc == WOTB_OK && cudaSetDevice(ctx->device) != cudaSuccess) rc = WOTB_ERR_CUDA;
     cudaStream_t st = ctx->stream;
@@ -410,6 +580,17 @@ int online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x1, in
     S->launches = 3;
     WOTB_CUDA(cudaGetLastError());
     *out = S;
+    return WOTB_OK;
+}
+
+// The flag exchange.  Ranks that are THREADS of one process on ONE GPU (the single-GPU test of the protocol) can share
+// a hardware work queue: a kernel of rank B may then sit behind rank A's next kernel, which waits for A's flag kernel,
+// which waits for B -- a false dependency the hardware cannot resolve.  With WOTB_PEER_HOST_SYNC=1 the host waits for
+// the flag kernel before it enqueues anything behind it, so a queue never holds a blocked kernel.  One process per
+// GPU (the product configuration) has no such coupling and leaves it off.
+inline int peer_barrier(OnlineSolve *S, cudaStream_t st, int gate) {
+    k_peer_barrier<<<1, 32, 0, st>>>(S->d_peer, S->d_ctrl, gate);
+    if (S->peer_host_sync) WOTB_CUDA(cudaStreamSynchronize(st));
     return WOTB_OK;
 }
 
@@ -436,19 +617,30 @@ int online_step(OnlineSolve *S, int op, double *exch) {
     const int I = (int)S->I, J = (int)S->J;
     const unsigned bi = (unsigned)cdiv(I, 256), bj = (unsigned)cdiv(J, 256);
     const bool dg = S->h.solver == WOTB_SOLVER_DUALITY_GAP;
+    PeerX *X = S->d_peer && S->V.peer ? S->d_peer : nullptr;
+    const int n_own = P.row_hi - P.row_lo;
+    const unsigned bown = (unsigned)cdiv(n_own > 0 ? n_own : 1, 256);
     switch (op) {
         case kOpBeginA:
             S->launches += P.pack(st, c);
             if (dg) {
-                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                WOTB_REQUIRE(exch != nullptr || X, "exchange buffer is NULL");
                 S->launches += P.s0_pass(st, V, c);
-                k_export_slice<<<bi, 256, 0, st>>>(V.sumK0_part, exch, I, P.row_lo, P.row_hi);
+                if (X) {
+                    if (n_own > 0) k_peer_push_slice<<<bown, 256, 0, st>>>(V.sumK0_part, P.row_lo, P.row_hi, X, c, 3);
+                } else {
+                    k_export_slice<<<bi, 256, 0, st>>>(V.sumK0_part, exch, I, P.row_lo, P.row_hi);
+                }
                 S->launches += 1;
             }
             S->launches += P.refresh_slots(st, V, c, 1);
             break;
         case kOpBeginB:
-            if (dg) {
+            if (dg && X) {
+                WOTB_TRY(peer_barrier(S, st, 3));
+                k_peer_import_vec<<<bi, 256, 0, st>>>(X, c, V.sumK0_part, I, 3);
+                S->launches += 1;
+            } else if (dg) {
                 WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
                 k_import_vec<<<bi, 256, 0, st>>>(c, exch, V.sumK0_part, I, 3);
             }
@@ -456,21 +648,33 @@ int online_step(OnlineSolve *S, int op, double *exch) {
             S->launches += 2;
             break;
         case kOpRow:
-            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            P.row_pass(st, V, c, 0, nullptr);
-            k_export_a_slice<<<bi, 256, 0, st>>>(V, c, exch, P.row_lo, P.row_hi);
-            S->launches += 2;
+            P.row_pass(st, V, c, 0, nullptr);  // peer mode: the finishing code stores (a, s) into every rank's buffer
+            S->launches += 1;
+            if (!X) {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                k_export_a_slice<<<bi, 256, 0, st>>>(V, c, exch, P.row_lo, P.row_hi);
+                S->launches += 1;
+            }
             break;
         case kOpColPartial:
-            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            WOTB_CUDA(cudaMemsetAsync(exch + 2 * (size_t)I, 0, (size_t)J * 8, st));
-            P.col_pass(st, V, c, 4, exch + 2 * (size_t)I);
+            if (X) {
+                P.col_pass(st, V, c, 4, nullptr);  // partial column sums go straight into every rank's buffer
+            } else {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                WOTB_CUDA(cudaMemsetAsync(exch + 2 * (size_t)I, 0, (size_t)J * 8, st));
+                P.col_pass(st, V, c, 4, exch + 2 * (size_t)I);
+            }
             S->launches += 1;
             break;
         case kOpColFinish:
-            WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
-            k_import_a<<<bi, 256, 0, st>>>(V, c, exch);
-            k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch + 2 * (size_t)I);
+            if (X) {
+                WOTB_TRY(peer_barrier(S, st, 0));
+                k_peer_finish<<<bi > bj ? bi : bj, 256, 0, st>>>(V, c, X);
+            } else {
+                WOTB_REQUIRE(exch != nullptr, "exchange buffer is NULL");
+                k_import_a<<<bi, 256, 0, st>>>(V, c, exch);
+                k_online_col_finish<<<bj, 256, 0, st>>>(V, c, exch + 2 * (size_t)I);
+            }
             S->launches += 2;
             break;
         case kOpGapRows:  // kept for ABI stability: the row sums of the gap now ride on kOpRow (lazy check)
@@ -489,6 +693,12 @@ int online_step(OnlineSolve *S, int op, double *exch) {
                 P.row_pass(st, V, c, 2, exch);
             }
             S->launches += 1;
+            if (X) {  // gather the slices through the peer buffers: exch[0:I] is complete on return
+                if (n_own > 0) k_peer_push_slice<<<bown, 256, 0, st>>>(exch, P.row_lo, P.row_hi, X, c, -1);
+                WOTB_TRY(peer_barrier(S, st, -1));
+                k_peer_import_vec<<<bi, 256, 0, st>>>(X, c, exch, I, -1);
+                S->launches += 3;
+            }
             break;
         default:
             WOTB_REQUIRE(false, "unknown online step");

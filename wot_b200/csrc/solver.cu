@@ -822,6 +822,7 @@ int carve_vectors(wotb_ctx *ctx, int64_t I, int64_t J, int64_t ldw, int n_row_bl
     V.tcXB = V.tcYB = nullptr;
     V.tc_kseg = 0;
     V.tc_nseg = 3;
+    V.peer = nullptr;
     WOTB_CUDA(cudaMemsetAsync(V.tile_counters, 0, (size_t)n_col_tiles * 4 + 64, ctx->stream));
     WOTB_CUDA(cudaMemsetAsync(V.sumK0_part, 0, (size_t)n_k0_part * 8 + 64, ctx->stream));
     *out = V;
@@ -1178,5 +1179,13 @@ void online_rows(OnlineSolve *S, int64_t *lo, int64_t *hi) {
     *lo = S->P.row_lo;
     *hi = S->P.row_hi;
 }
-void online_close(OnlineSolve *S) { delete S; }
+void online_close(OnlineSolve *S) {
+    if (S && S->d_peer) {
+        cudaSetDevice(S->ctx->device);
+        cudaFree(S->d_peer);
+    }
+    delete S;
+}
+int64_t online_peer_bytes_of(OnlineSolve *S, int world) { return (int64_t)online_peer_bytes(S->I, S->J, world); }
+int online_attach(OnlineSolve *S, int world, void *const *bufs) { return online_attach_peers(S, world, bufs); }
 }  // namespace wotb

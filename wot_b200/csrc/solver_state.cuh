@@ -57,6 +57,26 @@ struct SolveCtrl {
     double c1, c2;      // log2(e)/eps and log2(e)/(eps*median): exponents are formed in base 2
 };
 
+// ---- row-sharded solves exchanging over peer memory (NVLink / NVSwitch), see online_solve.cuh ------------------
+// Every rank owns one exchange buffer of identical layout that all peers have mapped (cudaIpc or plain pointers
+// inside one process).  The pass kernels' finishing code STORES a rank's results straight into every peer's
+// buffer while the pass is still running (a-slices and their row sums from the row half-step, partial column sums
+// from the column half-step), a one-warp kernel exchanges flags, and the finishing kernel adds the partial sums in
+// rank order -- the same bits on every rank, so the replicated state machine stays in lockstep.  Two copies of every
+// region, selected by the parity of `seq` (exchanges completed so far): a rank can be at most one exchange ahead of a
+// peer, so what it writes never lands in a copy the peer still reads.
+constexpr int kMaxPeers = 8;
+struct PeerX {
+    int rank, world;
+    unsigned long long seq;       // exchanges completed; identical on every rank at every exchange
+    unsigned int ticket;          // last-block detection of the importing kernels
+    unsigned char *buf[kMaxPeers];  // exchange buffers of all ranks (own included), byte pointers
+    long long off_flags;          // unsigned long long [2][kMaxPeers]: flag of rank w = seq + 1 once w's data has landed
+    long long off_a[2], off_s[2];  // double [I] each: gathered a / gathered row sums (also used for other row vectors)
+    long long off_t[2];           // double [world][ld_t]: every rank's partial column sums
+    long long ld_t;
+};
+
 // Pointers into the per-solve vector workspace (all device memory, fixed for the solve).
 struct SolveVecs {
     const double *p;  // G, row masses
@@ -86,4 +106,6 @@ struct SolveVecs {
     __half *tcXB, *tcYB;
     int tc_kseg;
     int tc_nseg;  // 3: fp16 hi/lo split (default); 6: precise mode, grid-aligned leading limb + two more limbs
+    // ---- row-sharded solve over peer memory only (NULL otherwise) ---------------------------------------------------
+    PeerX *peer;
 };

@@ -8,8 +8,9 @@ Two partitionings (BASELINE.json north_star):
    the reference (ot_model.py:182-201).  No collective sits on the data path.
 
 2. One very large pair is row-sharded: `sharded_online_solve` drives the stepping entry points of the
-   library (wotb_online_*): each rank computes its slice of rows with the online kernel and the ranks
-   exchange one float64 vector (2 I + J entries) per Sinkhorn iteration with an NCCL all-reduce over NVLink.
+   library (wotb_online_*): each rank computes its slice of rows with the online kernel; per Sinkhorn iteration
+   the ranks exchange their a-slices and partial column sums either inside the kernels over peer memory (NVLink
+   stores from the passes' finishing code, default) or with one NCCL all-reduce of 2 I + J float64 values.
 """
 from __future__ import annotations
 
@@ -254,6 +255,13 @@ def _sweep_solve_gpu(x0, x1, G, growth_iters=1, kernel="online", **params):
 OP_BEGIN_A, OP_BEGIN_B, OP_ROW, OP_COL_PARTIAL, OP_COL_FINISH, OP_GAP_ROWS, OP_CHECK, OP_FINAL_ROWS = range(8)
 
 
+def hi_rows(n, rank, world, block=256):
+    """rows of the slice of 256-row blocks rank `rank` owns (the split of wotb_online_open)"""
+    blocks = -(-n // block)
+    lo, hi = blocks * rank // world, blocks * (rank + 1) // world
+    return max(0, min(hi * block, n) - min(lo * block, n))
+
+
 def sharded_median(ctx, X0, X1, rank, world, group=None):
     """Exact np.median of the I*J squared distances (ot_model.py:252) with the one pass over the distances split over
     the ranks' row shards: every rank draws the same sample (the coordinates are replicated), counts and gathers its
@@ -297,7 +305,122 @@ def sharded_median(ctx, X0, X1, rank, world, group=None):
     return med.value
 
 
-def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, use_graph=True, **params):
+class DistComm:
+    """Host-side plumbing of a row-sharded solve over torch.distributed: rank / world, a barrier, an object
+    all-gather (IPC handles) and the NCCL all-reduce of the `exchange="nccl"` mode."""
+    in_process = False
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank, self.world = _rank_world(group)
+
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def all_gather_object(self, obj):
+        import torch.distributed as dist
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def all_reduce(self, tensor):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
+
+
+class ThreadComm:
+    """The same plumbing for `world` ranks that are THREADS of one process (each with its own library context and
+    stream, on one GPU or several): peer buffers are plain device pointers, there is no NCCL.  Used by the tests to run
+    the complete peer-memory protocol on a single GPU; make one with `ThreadComm.make(world)` and hand comm[r] to
+    rank r's thread."""
+    in_process = True
+
+    def __init__(self, rank, world, shared):
+        self.rank, self.world, self._sh = rank, world, shared
+
+    @classmethod
+    def make(cls, world):
+        shared = {"bar": threading.Barrier(world), "slots": [None] * world}
+        return [cls(r, world, shared) for r in range(world)]
+
+    def barrier(self):
+        self._sh["bar"].wait(timeout=120)
+
+    def all_gather_object(self, obj):
+        self._sh["slots"][self.rank] = obj
+        self.barrier()
+        out = list(self._sh["slots"])
+        self.barrier()
+        return out
+
+    def all_reduce(self, tensor):
+        raise RuntimeError("in-process ranks exchange over peer memory only")
+
+
+class _PeerBuffers:
+    """One exchange buffer per rank, mapped into every rank (wotb_peer_*): cudaIpc handles between processes, plain
+    pointers between threads of one process."""
+
+    def __init__(self, ctx, solve, comm):
+        from . import _lib
+        self.ctx, self.comm = ctx, comm
+        self.own = C.c_void_p()
+        self.opened = []
+        lib, h = ctx.lib, ctx.handle
+        nbytes = C.c_int64()
+        _lib.check(lib.wotb_online_peer_bytes(solve, comm.world, C.byref(nbytes)))
+        handle = (C.c_ubyte * 64)()
+        err = None
+        try:
+            _lib.check(lib.wotb_peer_alloc(h, nbytes.value, C.byref(self.own), handle))
+        except Exception as e:  # noqa: BLE001 -- every rank must reach the gathers below
+            err = repr(e)
+        mine = self.own.value if comm.in_process else bytes(handle)
+        infos = comm.all_gather_object((err, mine))
+        ptrs = (C.c_void_p * comm.world)()
+        if all(e is None for e, _ in infos):
+            for w, (_, item) in enumerate(infos):
+                if w == comm.rank or comm.in_process:
+                    ptrs[w] = self.own.value if w == comm.rank else item
+                    continue
+                try:
+                    p = C.c_void_p()
+                    buf = (C.c_ubyte * 64).from_buffer_copy(item)
+                    _lib.check(lib.wotb_peer_open(h, buf, C.byref(p)))
+                    self.opened.append(p)
+                    ptrs[w] = p.value
+                except Exception as e:  # noqa: BLE001
+                    err = repr(e)
+                    break
+            if err is None:
+                try:
+                    _lib.check(lib.wotb_online_attach_peers(solve, comm.world, ptrs))
+                except Exception as e:  # noqa: BLE001
+                    err = repr(e)
+        errs = [e for e in comm.all_gather_object(err) if e is not None] + [e for e, _ in infos if e is not None]
+        self.error = errs[0] if errs else None      # the same verdict on every rank (also the barrier after attach)
+        if self.error is not None:
+            self.close(barrier=False)
+
+    def close(self, barrier=True):
+        lib, h = self.ctx.lib, self.ctx.handle
+        for p in self.opened:
+            lib.wotb_peer_close(h, p)
+        self.opened = []
+        if barrier:
+            self.comm.barrier()                      # nobody frees a buffer a peer still has mapped
+        if self.own.value:
+            lib.wotb_peer_free(h, self.own)
+            self.own = C.c_void_p()
+
+
+def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers=None, use_graph=True, exchange="auto",
+                         comm=None, **params):
     """Solve one day-pair with its rows sharded over the ranks of `group` (online kernel, float64 state).
 
     x0 [I,d], x1 [J,d], G [I]: the full arrays on every rank (NumPy or CUDA tensors).  Returns a dict with
@@ -312,13 +435,25 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
     the device when its work is not due, so all ranks replay the same graph the same number of times.
     `timers` (dict, optional) receives allreduce_us_per_iter (CUDA events around 20 all-reduces of the per-iteration
     payload on the solve's stream), allreduce_bytes and the launch mode.
+
+    exchange: "nccl" = the all-reduce described above; "peer" = no collective at all: the pass kernels store their
+    results into every rank's exchange buffer over NVLink while they run, one warp exchanges flags, one kernel adds
+    the partial column sums in rank order (include/wot_b200.h, wotb_online_attach_peers); "auto" = peer when the buffers
+    can be mapped on every rank (cudaIpc), else nccl.  WOTB_SHARD_EXCHANGE overrides "auto".
+    comm: DistComm(group) by default; ThreadComm for ranks that are threads of one process.
     """
     import torch
-    import torch.distributed as dist
 
     from . import _lib
 
-    rank, world = _rank_world(group)
+    comm = comm or DistComm(group)
+    rank, world = comm.rank, comm.world
+    if exchange == "auto":
+        exchange = os.environ.get("WOTB_SHARD_EXCHANGE", "auto")
+    if exchange not in ("auto", "peer", "nccl"):
+        raise ValueError("exchange must be 'auto', 'peer' or 'nccl'")
+    if world == 1 or world > 8:
+        exchange = "nccl"
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(device)
@@ -341,6 +476,8 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         median = params.pop("median", None)
         median_ms = 0.0
         if median is None:
+            if comm.in_process:
+                raise ValueError("in-process ranks need the median passed in")
             mev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             mev[0].record(stream)
             median = sharded_median(ctx, X0, X1, rank, world, group)
@@ -356,12 +493,23 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         _lib.check(lib.wotb_online_open(h, P(X0), n_i, P(X1), n_j, d, median, P(Gd), C.byref(prm), rank, world, P(f),
                                         P(g), C.byref(solve)))
 
+        peers = None
+        if exchange in ("auto", "peer"):
+            stream.synchronize()
+            peers = _PeerBuffers(ctx, solve, comm)
+            if peers.error is not None:
+                if exchange == "peer":
+                    lib.wotb_online_close(solve)
+                    raise RuntimeError("peer-memory exchange unavailable: " + peers.error)
+                peers = None
+        exchange = "peer" if peers is not None else "nccl"
+
         def step(op):
             _lib.check(lib.wotb_online_step(solve, op, P(exch)))
 
         def reduce(n):
-            if world > 1:
-                dist.all_reduce(exch[:n], op=dist.ReduceOp.SUM, group=group)
+            if world > 1 and peers is None:
+                comm.all_reduce(exch[:n])
 
         slots = 5 if solver == _lib.SOLVER_DUALITY_GAP else 10
 
@@ -386,7 +534,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         graph = None
         try:
-            if world > 1:
+            if world > 1 and peers is None:
                 reduce(n_i)                       # NCCL communicator and channels exist before timing / capture
                 exch.zero_()
             ev[0].record(stream)
@@ -410,9 +558,15 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
             lo, hi = C.c_int64(), C.c_int64()
             _lib.check(lib.wotb_online_rows(solve, C.byref(lo), C.byref(hi)))
             if timers is not None:
-                timers["mode"] = "cuda graph per batch (NCCL captured)" if graph is not None else "stepwise launches"
-                timers["allreduce_bytes"] = (2 * n_i + n_j) * 8
-                if world > 1:
+                timers["exchange"] = exchange
+                if peers is not None:
+                    timers["mode"] = ("cuda graph per batch" if graph is not None else "stepwise launches") + \
+                        ", peer-memory exchange (stores from the passes' finishing code, flag barrier, no collective)"
+                    timers["peer_bytes_out_per_iter"] = (world - 1) * (2 * (hi_rows(n_i, rank, world)) + n_j) * 8
+                else:
+                    timers["mode"] = "cuda graph per batch (NCCL captured)" if graph is not None else "stepwise launches"
+                    timers["allreduce_bytes"] = (2 * n_i + n_j) * 8
+                if world > 1 and peers is None:
                     probe = torch.zeros(2 * n_i + n_j, dtype=torch.float64, device=dev)
                     te = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                     for _ in range(3):
@@ -425,6 +579,9 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                     timers["allreduce_us_per_iter"] = te[0].elapsed_time(te[1]) * 1e3 / 20
         finally:
             del graph
+            stream.synchronize()
+            if peers is not None:
+                peers.close()
             lib.wotb_online_close(solve)
         out_info = info.as_dict()
         out_info["gpu_ms"] = ev[0].elapsed_time(ev[1])
