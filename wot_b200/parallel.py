@@ -570,10 +570,10 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                     probe = torch.zeros(2 * n_i + n_j, dtype=torch.float64, device=dev)
                     te = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                     for _ in range(3):
-                        dist.all_reduce(probe, op=dist.ReduceOp.SUM, group=group)
+                        comm.all_reduce(probe)
                     te[0].record(stream)
                     for _ in range(20):
-                        dist.all_reduce(probe, op=dist.ReduceOp.SUM, group=group)
+                        comm.all_reduce(probe)
                     te[1].record(stream)
                     te[1].synchronize()
                     timers["allreduce_us_per_iter"] = te[0].elapsed_time(te[1]) * 1e3 / 20
