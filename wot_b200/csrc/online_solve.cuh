@@ -61,7 +61,7 @@ struct OnlinePasses {
         const size_t o_ps = take((size_t)ldi * 8), o_qs = take((size_t)ldj * 8);
         const size_t o_pd = take((size_t)ldi * 8), o_qd = take((size_t)ldj * 8);
         const size_t o_p0 = take((size_t)ldi * 8), o_q0 = take((size_t)ldj * 8);
-        const size_t o_cnt = take((size_t)(ldi + ldj) / kOnTile * 4 + 64);
+        const size_t o_cnt = take((size_t)(ldi + ldj) / 32 * 4 + 64);  // tcgen05 pass: one counter per 32 rows (tc_publish)
         size_t o_xt = 0, o_yt = 0, o_part = 0, o_xa = 0, o_xb = 0, o_ya = 0, o_yb = 0, o_rx = 0, o_ry = 0, o_geo = 0;
         int nseg_row = 1, nseg_col = 1, seg_tiles_row = 1, seg_tiles_col = 1, slots_row = 1, slots_col = 1;
         if (tc) {
@@ -93,8 +93,8 @@ struct OnlinePasses {
         nx = (double *)(ob + o_nx), ny = (double *)(ob + o_ny);
         P0 = (double *)(ob + o_p0), Q0 = (double *)(ob + o_q0);
         part = (double *)(ob + o_part);
-        unsigned int *cnt_i = (unsigned int *)(ob + o_cnt), *cnt_j = cnt_i + ldi / kOnTile;
-        WOTB_CUDA(cudaMemsetAsync(cnt_i, 0, (size_t)(ldi + ldj) / kOnTile * 4, st));
+        unsigned int *cnt_i = (unsigned int *)(ob + o_cnt), *cnt_j = cnt_i + ldi / 32;
+        WOTB_CUDA(cudaMemsetAsync(cnt_i, 0, (size_t)(ldi + ldj) / 32 * 4, st));
         V->online = 1;
         V->nx = nx, V->ny = ny;
         V->Ps = (double *)(ob + o_ps), V->Qs = (double *)(ob + o_qs);

@@ -394,8 +394,8 @@ struct TcArgs {
     int in_tile0;         // first in tile (128 rows) that is reduced over
     int in_ntiles;        // number of in tiles reduced over
     int n_stages;         // B ring depth
-    double *part;         // [slots][out_ld] partial sums, one slot per CTA that contributes to an out block
-    unsigned int *counters;  // one per out block
+    double *part;         // [slots][out_ld] partial sums, one slot per (CTA that contributes to an out block, column half)
+    unsigned int *counters;  // kTcRowBlocks * 4 per out block: one per group of 32 rows (tc_publish)
     int dbg;              // measurement only: bit0 skip the MMAs, bit1 skip the exp2 work, bit3 write cycle counters
     long long *prof;      // [CTA][epilogue warp][4]: cycles total, waiting for accumulators, waiting for tcgen05.ld, tiles
 };
@@ -432,6 +432,22 @@ __device__ __forceinline__ void tcb_wait(uint32_t bar, uint32_t parity) {
         if (!ok && ++spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
     } while (!ok);
 }
+// non-blocking phase test (test_wait never suspends the thread): issued early, consumed later, so that the ~200 clocks a
+// barrier query takes on this part are spent under arithmetic instead of in front of it
+__device__ __forceinline__ uint32_t tcb_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok;
+}
+// makes a value opaque to the compiler: it stays in its register instead of being re-derived (S2UR SR_CgaCtaId / ULEA
+// chains in front of every barrier access, profiles/r2p)
+__device__ __forceinline__ uint32_t tc_keep(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
+}
 __device__ __forceinline__ void tcb_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -439,6 +455,66 @@ __device__ __forceinline__ void tcb_bulk_g2s(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void tcb_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- publish / finish, one WARP at a time ------------------------------------------------------------------------
+// A warp owns 32 rows of an out block (x all or half of the columns of every tile).  When its CTA's share of the
+// block is complete it stores its 32 partial sums into its own slot (CTA within the block, column half), fences,
+// and takes a ticket on the counter of (block, row group).  The warp that draws the last ticket adds the slots --
+// per CTA the two column halves first, then the CTAs in order, so the result does not depend on timing -- and
+// applies the update to its 32 rows.  No CTA-wide barrier: the other warps of the CTA are already in the next block's
+// tiles, and the eight row groups of a block are finished by (up to) eight different warps in parallel.
+// (Round 1/2 did this per CTA behind three named barriers: 5.4k clocks per CTA and pass, profiles/r2p.)
+template <bool COLPASS, int EW>
+__device__ __forceinline__ void tc_publish(const TcArgs &A, const SolveVecs &V, SolveCtrl *ctrl, int mode, double *rowsum_out,
+                                           int b, int nt, long long T, int G, int rb, int q, int h, int lane, double acc,
+                                           bool async_fence) {
+    constexpr int H = EW / 4;  // column halves = contributions per CTA and row
+    const int blk = A.out_blk0 + b;
+    const long long row = (long long)blk * kTcOut + rb * kTcM + q * 32 + lane;
+    const int c_first = tc_cta_of_unit((long long)b * nt, T, G);
+    const int c_last = tc_cta_of_unit((long long)(b + 1) * nt - 1, T, G);
+    const int n_cta = c_last - c_first + 1;
+    A.part[((long long)((int)blockIdx.x - c_first) * H + h) * A.out_ld + row] = acc;
+    __threadfence();
+    __syncwarp();
+    unsigned int *counter = A.counters + ((long long)blk * (kTcRowBlocks * 4) + rb * 4 + q);
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counter, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != (unsigned int)(n_cta * H - 1)) return;
+    __threadfence();
+    double vmax = 0.0;
+    if (row < A.out_n) {
+        double sum = 0.0;
+        for (int sl = 0; sl < n_cta; ++sl) {
+            const double *p = A.part + (long long)sl * H * A.out_ld + row;
+            double t = __ldcg(p);
+            if (H == 2) t += __ldcg(p + A.out_ld);
+            sum += t;
+        }
+        sum *= exp2(A.resid[row]);
+        vmax = online_apply<COLPASS>(mode, (int)row, sum, V, ctrl, rowsum_out);
+        // persistent batch kernel: the offset slots just written are read by other CTAs' TMA loads after the grid barrier
+        if (async_fence) asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
+    if (mode == 0) {
+        vmax = warp_max(vmax);
+        if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+        *counter = 0;
+        if (mode == 0 && COLPASS) {
+            const unsigned int done = atomicAdd(&ctrl->col_tiles_done, 1u);
+            if (done == (unsigned int)(A.n_blocks * (kTcRowBlocks * 4) - 1)) {
+                __threadfence();
+                ctrl->col_tiles_done = 0;
+                close_iteration(ctrl);
+            }
+        }
+    }
 }
 
 // One pass = (out blocks) x (in tiles) work units of 256 x 128 entries, dealt to the CTAs of a one-wave
@@ -456,14 +532,12 @@ template <bool COLPASS, int KSEG, int EW, int NSEG, bool PROF>
 __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     k_online_tc(TcArgs A, SolveVecs V, SolveCtrl *ctrl, int mode, double *rowsum_out) {
     constexpr int RB = kTcRowBlocks, NT = kTcN;
-    constexpr int kEpiThreads = RB * EW * 32;
     constexpr int NCH = 4 / (EW / 4);  // 32-column chunks per tile and warp
     constexpr int kseg = KSEG;
     constexpr int NABUF = NSEG == 3 ? 2 : 1;
     constexpr uint32_t row_bytes = (uint32_t)kseg * NSEG * 2u;
     constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    __shared__ int is_last;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int S = A.n_stages;
     // shared memory map (32-bit shared addresses): barriers + reduction scratch (kTcTail bytes, at fixed offsets so
@@ -477,7 +551,6 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     const uint32_t b_af = b_acce + 8 * 2 * RB, b_ae = b_af + 16;
     unsigned char *bars_p = tc_smem + (bars - smem0);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars_p + 8 * (2 * kTcMaxStages + 4 * RB + 4));
-    double *red = reinterpret_cast<double *>(bars_p) + 32;  // [RB * 128]: second column half of every row (EW == 8)
 
     const int nt = A.in_ntiles;
     const long long T = (long long)A.n_blocks * nt;
@@ -589,14 +662,15 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             const uint64_t descA = descA0 + (uint64_t)(((uint32_t)(abuf * RB + rb) * a_bytes) >> 4);
             for (int k = 0; k < n_in_seg; ++k, ++u) {
                 const uint32_t buf = u & 1u, par = (u >> 1) & 1u;
+                // the B tile first (it landed long ago: the query's latency is spent while the epilogue still holds the
+                // accumulator), then the accumulator: the MMAs go out as soon as the epilogue lets go of it
+                TC_M0();
+                tcb_wait(b_full + 8 * s, full_par);
+                TC_M1(m_full);
                 TC_M0();
                 tcb_wait(b_acce + 8 * (buf * RB + rb), par ^ 1u);
                 __syncwarp();
                 TC_M1(m_acc);
-                TC_M0();
-                tcb_wait(b_full + 8 * s, full_par);
-                __syncwarp();
-                TC_M1(m_full);
                 tc_fence_after();
                 TC_M0();
                 const uint64_t descB = descB0 + (uint64_t)(((uint32_t)s * b_bytes) >> 4);
@@ -640,8 +714,8 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
         const uint32_t n_units = (uint32_t)(g1 - g0);
         // loop-carried addresses: accumulator buffer `cur` of this row block (TMEM columns and the two barriers);
         // the other buffer is reached by XOR with the precomputed differences
-        const uint32_t t_buf0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32));
-        const uint32_t accf0 = b_accf + 8 * rb, acce0 = b_acce + 8 * rb;
+        const uint32_t t_buf0 = tc_keep(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rb * NT + h * (NCH * 32)));
+        const uint32_t accf0 = tc_keep(b_accf + 8 * rb), acce0 = tc_keep(b_acce + 8 * rb);
         constexpr uint32_t kBufBar = 8 * RB;  // barrier distance between buffer 0 and buffer 1
         if (!skip_exp) {
             tcb_wait(accf0, 0);
@@ -669,6 +743,11 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                     continue;
                 }
                 float tile_sum = 0.f;
+                // is the NEXT unit's accumulator complete?  (the MMA warp runs a unit ahead, so normally yes.)  Asked here,
+                // answered while this unit's first columns are evaluated
+                // (asked unconditionally -- after the last unit the answer is simply not used -- so that the query sits in
+                // the same basic block as the arithmetic and can be scheduled in front of it)
+                const uint32_t next_ok = tcb_test(accf0 + (buf ^ 1u) * kBufBar, ((u + 1) >> 1) & 1u);
 #pragma unroll
                 for (int c = 0; c < NCH; c += 2) {
                     TC_T0();
@@ -690,7 +769,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                         if (u + 1 < n_units) {
                             const uint32_t nb = buf ^ 1u;
                             TC_T0();
-                            tcb_wait(accf0 + nb * kBufBar, ((u + 1) >> 1) & 1u);
+                            if (!next_ok) tcb_wait(accf0 + nb * kBufBar, ((u + 1) >> 1) & 1u);
                             TC_T1(c_acc);
                             tc_fence_after();
                             WOTB_TMEM_LD32(va, t_buf0 + nb * kTcAccCols);
@@ -703,54 +782,9 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
             acc += (double)facc;
             }
             g += n_in_seg;
-            // ---- this CTA's share of out block b is complete: publish it, and finish the block if it is the last ----
+            // ---- this CTA's share of out block b is complete: publish it, and finish the rows if it was the last ----
             TC_T0();
-            const int blk = A.out_blk0 + b;
-            const long long row = (long long)blk * kTcOut + rb * kTcM + q * 32 + lane;
-            const int c_first = tc_cta_of_unit((long long)b * nt, T, G);
-            const int c_last = tc_cta_of_unit((long long)(b + 1) * nt - 1, T, G);
-            if (EW == 8) {
-                if (h == 1) red[rb * kTcM + q * 32 + lane] = acc;
-                named_bar_sync(1, kEpiThreads);
-                if (h == 0) acc += red[rb * kTcM + q * 32 + lane];
-            }
-            if (h == 0) A.part[(long long)((int)blockIdx.x - c_first) * A.out_ld + row] = acc;
-            __threadfence();
-            named_bar_sync(1, kEpiThreads);
-            if (ew == 0 && lane == 0) {
-                const unsigned int ticket = atomicAdd(&A.counters[blk], 1u);
-                is_last = ticket == (unsigned int)(c_last - c_first);
-            }
-            named_bar_sync(1, kEpiThreads);
-            if (is_last) {
-                __threadfence();
-                double vmax = 0.0;
-                if (h == 0) {
-                    if (row < A.out_n) {
-                        double sum = 0.0;
-                        for (int sl = 0; sl <= c_last - c_first; ++sl) sum += __ldcg(A.part + (long long)sl * A.out_ld + row);
-                        sum *= exp2(A.resid[row]);
-                        vmax = online_apply<COLPASS>(mode, (int)row, sum, V, ctrl, rowsum_out);
-                    }
-                    if (mode == 0) {
-                        vmax = warp_max(vmax);
-                        if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
-                    }
-                }
-                __threadfence();
-                named_bar_sync(1, kEpiThreads);
-                if (ew == 0 && lane == 0) {
-                    A.counters[blk] = 0;
-                    if (mode == 0 && COLPASS) {
-                        const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
-                        if (ticket == (unsigned int)(A.n_blocks - 1)) {
-                            __threadfence();
-                            ctrl->col_tiles_done = 0;
-                            close_iteration(ctrl);
-                        }
-                    }
-                }
-            }
+            tc_publish<COLPASS, EW>(A, V, ctrl, mode, rowsum_out, b, nt, T, G, rb, q, h, lane, acc, false);
             TC_T1(c_fin);
         }
         if (PROF && prof && lane == 0) {
@@ -794,14 +828,12 @@ template <int KSEG, int EW, int NSEG>
 __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     k_online_batch(TcArgs Arow, TcArgs Acol, SolveVecs V, SolveCtrl *ctrl, int n_iters) {
     constexpr int RB = kTcRowBlocks, NT = kTcN;
-    constexpr int kEpiThreads = RB * EW * 32;
     constexpr int NCH = 4 / (EW / 4);
     constexpr int kseg = KSEG;
     constexpr int NABUF = NSEG == 3 ? 2 : 1;
     constexpr uint32_t row_bytes = (uint32_t)kseg * NSEG * 2u;
     constexpr uint32_t a_bytes = kTcM * row_bytes, b_bytes = NT * row_bytes;
     extern __shared__ __align__(128) unsigned char tc_smem[];
-    __shared__ int is_last;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int S = Arow.n_stages;
     const uint32_t smem0 = smem_u32(tc_smem);
@@ -812,7 +844,6 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
     const uint32_t b_acce = b_accf + 8 * 2 * RB;
     const uint32_t b_af = b_acce + 8 * 2 * RB, b_ae = b_af + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tc_smem + 8 * (2 * kTcMaxStages + 4 * RB + 4));
-    double *red = reinterpret_cast<double *>(tc_smem) + 32;
     const int G = gridDim.x;
 
     if (tid == 0) {
@@ -983,54 +1014,11 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                     acc += (double)facc;
                 }
                 g += n_in_seg;
-                // ---- publish this CTA's share of out block b; the last CTA to arrive finishes the block ----
-                const int blk = A.out_blk0 + b;
-                const long long row = (long long)blk * kTcOut + rb * kTcM + q * 32 + lane;
-                const int c_first = tc_cta_of_unit((long long)b * nt, T, G);
-                const int c_last = tc_cta_of_unit((long long)(b + 1) * nt - 1, T, G);
-                if (EW == 8) {
-                    if (h == 1) red[rb * kTcM + q * 32 + lane] = acc;
-                    named_bar_sync(1, kEpiThreads);
-                    if (h == 0) acc += red[rb * kTcM + q * 32 + lane];
-                }
-                if (h == 0) A.part[(long long)((int)blockIdx.x - c_first) * A.out_ld + row] = acc;
-                __threadfence();
-                named_bar_sync(1, kEpiThreads);
-                if (ew == 0 && lane == 0) {
-                    const unsigned int ticket = atomicAdd(&A.counters[blk], 1u);
-                    is_last = ticket == (unsigned int)(c_last - c_first);
-                }
-                named_bar_sync(1, kEpiThreads);
-                if (is_last) {
-                    __threadfence();
-                    double vmax = 0.0;
-                    if (h == 0) {
-                        if (row < A.out_n) {
-                            double sum = 0.0;
-                            for (int sl = 0; sl <= c_last - c_first; ++sl) sum += __ldcg(A.part + (long long)sl * A.out_ld + row);
-                            sum *= exp2(A.resid[row]);
-                            vmax = col ? online_apply<true>(0, (int)row, sum, V, ctrl, nullptr)
-                                       : online_apply<false>(0, (int)row, sum, V, ctrl, nullptr);
-                            // the offset slots just written are read by other CTAs' TMA loads after the grid barrier
-                            asm volatile("fence.proxy.async.global;" ::: "memory");
-                        }
-                        vmax = warp_max(vmax);
-                        if (lane == 0) atomic_max_nonneg(&ctrl->maxabs, vmax);
-                    }
-                    __threadfence();
-                    named_bar_sync(1, kEpiThreads);
-                    if (ew == 0 && lane == 0) {
-                        A.counters[blk] = 0;
-                        if (col) {
-                            const unsigned int ticket = atomicAdd(&ctrl->col_tiles_done, 1u);
-                            if (ticket == (unsigned int)(A.n_blocks - 1)) {
-                                __threadfence();
-                                ctrl->col_tiles_done = 0;
-                                close_iteration(ctrl);
-                            }
-                        }
-                    }
-                }
+                // ---- publish this CTA's share of out block b; the last warp to arrive at its rows finishes them ----
+                if (col)
+                    tc_publish<true, EW>(A, V, ctrl, 0, nullptr, b, nt, T, G, rb, q, h, lane, acc, true);
+                else
+                    tc_publish<false, EW>(A, V, ctrl, 0, nullptr, b, nt, T, G, rb, q, h, lane, acc, true);
             }
         }
         // ---- end of the half-step: every partial is published, every block finished, the iteration possibly closed ----
@@ -1080,7 +1068,7 @@ inline TcPlan tc_plan(int d, int ew = 4, int nseg = 3, bool prof = false) {
 inline int tc_grid(int sm_count, int n_blocks, int in_tiles, int *max_slots) {
     const long long T = (long long)n_blocks * in_tiles;
     const int G = (int)(T < sm_count ? T : sm_count);
-    *max_slots = (int)cdiv(G, n_blocks) + 1;
+    *max_slots = 2 * ((int)cdiv(G, n_blocks) + 1);  // x 2 column halves (16 epilogue warps)
     return G;
 }
 
@@ -1251,14 +1239,14 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
         grid_used = grid;
         const size_t o_ao = take(po * row_bytes), o_bo = take(po * row_bytes), o_ai = take(pi * row_bytes),
                      o_bi = take(pi * row_bytes), o_res = take(po * 8), o_part = take((size_t)max_slots * po * 8),
-                     o_cnt = take((size_t)out_blocks * 4 + 64), o_geo = take(sizeof(TcGeo));
+                     o_cnt = take((size_t)out_blocks * 32 + 64), o_geo = take(sizeof(TcGeo));
         WOTB_TRY(ctx->onl.reserve(off));
         char *ob = ctx->onl.as<char>();
         __half *Ao = (__half *)(ob + o_ao), *Bo = (__half *)(ob + o_bo), *Ai = (__half *)(ob + o_ai), *Bi = (__half *)(ob + o_bi);
         double *resid = (double *)(ob + o_res), *part = (double *)(ob + o_part);
         unsigned int *cnt = (unsigned int *)(ob + o_cnt);
         TcGeo *geo = (TcGeo *)(ob + o_geo);
-        WOTB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)out_blocks * 4, st));
+        WOTB_CUDA(cudaMemsetAsync(cnt, 0, (size_t)out_blocks * 32, st));
         WOTB_CUDA(cudaMemsetAsync(geo, 0, sizeof(TcGeo), st));
         k_tc_geo<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(x_out, (int)n_out, d, geo, 0);
         k_tc_geo<<<(unsigned)cdiv(n_in, 256), 256, 0, st>>>(x_in, (int)n_in, d, geo, 1);
