@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libwot_b200.so")
 SOURCES = ["api.cu", "solver.cu", "cost.cu", "pca.cu"]
-HEADERS = ["common.cuh", "solver_state.cuh", "fused_iter.cuh", "online_pass.cuh", "online_tc.cuh", "online_solve.cuh", os.path.join("..", "..", "include", "wot_b200.h")]
+HEADERS = ["common.cuh", "solver_state.cuh", "fused_iter.cuh", "fused_cluster.cuh", "online_pass.cuh", "online_tc.cuh", "online_solve.cuh", os.path.join("..", "..", "include", "wot_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

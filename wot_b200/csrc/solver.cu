@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(kColThreads) k_col(const float *__restrict__ K
 
 }  // namespace wotb
 #include "fused_iter.cuh"
+#include "fused_cluster.cuh"
 namespace wotb {
 
 // ------------------------------------------------------------------------------------------------
@@ -343,9 +344,7 @@ struct CheckCluster {
     unsigned n_red;
 };
 
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// cluster_sync_all: fused_cluster.cuh
 
 __device__ __forceinline__ double ld_dsmem(const double *local, unsigned rank) {
     uint32_t addr = (uint32_t)__cvta_generic_to_shared(local), remote;
@@ -1029,19 +1028,30 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
     const int slots = h.solver == WOTB_SOLVER_DUALITY_GAP ? 5 : 10;
     volatile int *host_done = ctx->status.as<int>();
     const FusePlan plan = (prm->reserved & 1) ? FusePlan() : plan_fused(ctx, I, ld);
+    // rows too wide for one CTA (J > 23k): a thread-block cluster shares every row (fused_cluster.cuh)
+    FuseClusterPlan cplan = ((prm->reserved & 1) || plan.ok) ? FuseClusterPlan() : plan_fused_cluster(ctx, I, ld);
     float *part_f = ctx->part.as<float>();
-    if (plan.ok) {  // sets the dynamic shared memory attribute outside of any stream capture
+    if (plan.ok || cplan.ok) {  // sets the dynamic shared memory attribute outside of any stream capture
         SolveCtrl idle = h;
         idle.done = 1;
         WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &idle, sizeof(idle), cudaMemcpyHostToDevice, st));
-        WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f, 1));
+        if (plan.ok) {
+            WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f, 1));
+        } else if (launch_fused_cluster(cplan, st, K, ld, V, d_ctrl, part_f, 1) != WOTB_OK ||
+                   cudaStreamSynchronize(st) != cudaSuccess) {
+            cudaGetLastError();  // the cluster + cooperative launch is not available here: two sweeps per iteration
+            cplan.ok = false;
+        }
         WOTB_CUDA(cudaMemcpyAsync(d_ctrl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
         launch_init(ctx, V, d_ctrl, ld);
     }
+    const bool one_launch = plan.ok || cplan.ok;
     auto sequence = [&]() {
         k_build<<<build_grid, kBuildThreads, 0, st>>>(C, ldc, K, ld, V, d_ctrl);
         if (plan.ok) {
             launch_fused(plan, st, K, ld, V, d_ctrl, part_f, slots);  // one cooperative launch per batch
+        } else if (cplan.ok) {
+            launch_fused_cluster(cplan, st, K, ld, V, d_ctrl, part_f, slots);
         } else {
             for (int s = 0; s < slots; ++s) {
                 k_row<<<row_grid, kRowThreads, 0, st>>>(K, ld, V, d_ctrl, 0, nullptr);
@@ -1050,9 +1060,9 @@ int sinkhorn_stored(wotb_ctx *ctx, const float *C, int64_t ldc, int64_t I, int64
         }
         launch_check(ctx, V, d_ctrl, host_done);
     };
-    const int per_seq = 2 + (plan.ok ? 1 : 2 * slots);
+    const int per_seq = 2 + (one_launch ? 1 : 2 * slots);
     info->launches = 1;
-    int rc = pump(ctx, prm->use_graph != 0, per_seq, plan.ok ? 1 : 2 * slots, sequence, info);
+    int rc = pump(ctx, prm->use_graph != 0, per_seq, one_launch ? 1 : 2 * slots, sequence, info);
     if (rc != WOTB_OK) return rc;
 
     WOTB_CUDA(cudaMemcpyAsync(&h, d_ctrl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1141,18 +1151,23 @@ int bench_matvec(wotb_ctx *ctx, int64_t I, int64_t J, int reps, double *ms_row, 
     if (ms_fused) {
         *ms_fused = -1.0;
         const FusePlan plan = plan_fused(ctx, I, ld);
-        if (plan.ok) {
+        const FuseClusterPlan cplan = plan.ok ? FuseClusterPlan() : plan_fused_cluster(ctx, I, ld);
+        if (plan.ok || cplan.ok) {
             float *part_f = ctx->part.as<float>();
             const int per_launch = 5;
             SolveCtrl zero_bar = h;
             auto reset = [&]() { return cudaMemcpyAsync(d_ctrl, &zero_bar, sizeof(zero_bar), cudaMemcpyHostToDevice, st); };
+            auto run = [&]() {
+                return plan.ok ? launch_fused(plan, st, K, ld, V, d_ctrl, part_f, per_launch)
+                               : launch_fused_cluster(cplan, st, K, ld, V, d_ctrl, part_f, per_launch);
+            };
             WOTB_CUDA(reset());
-            WOTB_TRY(launch_fused(plan, st, K, ld, V, d_ctrl, part_f, per_launch));
+            WOTB_TRY(run());
             const int launches = (reps + per_launch - 1) / per_launch;
             WOTB_CUDA(reset());
             WOTB_CUDA(cudaEventRecord(ctx->ev0, st));
             for (int r = 0; r < launches; ++r) {
-                launch_fused(plan, st, K, ld, V, d_ctrl, part_f, per_launch);
+                run();
                 k_fill<<<1, 32, 0, st>>>((float *)&d_ctrl->grid_bar, 1, 0.f);  // what k_build does in a solve
             }
             WOTB_CUDA(cudaEventRecord(ctx->ev1, st));
