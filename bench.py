@@ -404,9 +404,12 @@ def c3_block(torch, local_rank, mufu_peak, hbm_peak, n=50000):
                    "workspace_gb": lib.wotb_workspace_bytes(h) / 1e9}
             if kernel == "stored":
                 ld = (n + 31) // 32 * 32
-                sweeps = 1 if n <= 23040 else 2          # rows beyond 23k columns do not fit the fused kernel's ring
+                # K is read once per iteration: one CTA per row up to 23,040 columns (k_fused), a thread-block cluster
+                # per row beyond (k_fused_cl, csrc/fused_cluster.cuh; round 1 / early round 2 needed two sweeps here)
+                sweeps = 1
                 gbs = sweeps * n * ld * 4 * i["iters"] / sec / 1e9
-                rec.update(hbm_gbs_all_in=gbs, hbm_frac_all_in=gbs / hbm_peak, k_sweeps_per_iter=sweeps)
+                rec.update(hbm_gbs_all_in=gbs, hbm_frac_all_in=gbs / hbm_peak, k_sweeps_per_iter=sweeps,
+                           kernel="k_fused" if n <= 23040 else "k_fused_cl (cluster of 2-8 CTAs per row)")
             else:
                 texp = 2.0 * n * n * i["iters"] / sec / 1e12
                 rec.update(texp_per_s_all_in=texp, mufu_frac_all_in=texp / mufu_peak)
