@@ -808,9 +808,10 @@ def test_cli_optimal_transport_end_to_end(ot, tmp_path):
     assert list(g.columns) == ["g0", "g1", "g2"] and len(g) == 260 + 300
 
 
-def test_gpu_pca_rank_deficient_input_is_handed_to_sklearn(caplog):
+def test_gpu_pca_rank_deficient_input_takes_the_exact_gpu_solver(caplog):
     """An expression matrix of rank 20 cannot feed 40 independent test vectors: the Cholesky-QR of the range finder
-    reports it, backend='gpu' raises, backend='auto' logs a warning and returns scikit-learn's result."""
+    reports it, backend='gpu' raises, backend='auto' logs a warning and returns the exact GPU solver's result: the
+    components of the non-zero singular values equal scikit-learn's, nothing is computed on the CPU."""
     import logging
     from wot_b200.ot import util
     rng = np.random.default_rng(0)
@@ -820,5 +821,34 @@ def test_gpu_pca_rank_deficient_input_is_handed_to_sklearn(caplog):
         util.compute_pca(m1, m2, 30, backend="gpu")
     with caplog.at_level(logging.WARNING, logger="wot"):
         p1, p2, pca, _ = util.compute_pca(m1, m2, 30)
-    assert "rank-deficient" in caplog.text and not isinstance(pca, util.LocalPCA)
+    assert "rank-deficient" in caplog.text and isinstance(pca, util.LocalPCA)
     assert p1.shape == (600, 30) and p2.shape == (700, 30)
+    s1, s2, ref, _ = util.compute_pca_sklearn(m1, m2, 30)
+    np.testing.assert_allclose(pca.singular_values_[:18], ref.singular_values_[:18], rtol=1e-9)
+    np.testing.assert_allclose(np.vstack([p1, p2])[:, :18], np.vstack([s1, s2])[:, :18], rtol=0, atol=1e-8)
+    assert np.all(np.isfinite(p1)) and np.all(np.isfinite(p2))
+
+
+@pytest.mark.parametrize("cells,genes,k,solver", [([60, 70], 2000, 30, "covariance_eigh"), ([100, 120], 400, 30, "full"),
+                                                  ([15, 18], 600, 30, "full"), ([300, 350], 36, 30, "full"),
+                                                  ([400, 500], 9500, 30, "covariance_eigh")])
+def test_gpu_pca_exact_solver_shapes_vs_sklearn(cells, genes, k, solver):
+    """The shapes where scikit-learn's svd_solver='auto' leaves its randomized solver (few cells: covariance_eigh; tiny
+    or k close to the rank: full LAPACK SVD): compute_pca stays on the GPU (exact path) and equals scikit-learn."""
+    from oracle import wot_oracle
+    from wot_b200 import synthetic
+    from wot_b200.ot import util
+    X, day, _ = synthetic.expression_matrix(cells, n_genes=genes, seed=11)
+    m1, m2 = X[day == 0], X[day == 1]
+    kk = min(k, sum(cells))
+    assert util.sklearn_solver_choice(genes, sum(cells), kk) == solver
+    p1, p2, pca, mu = util.compute_pca_sklearn(m1, m2, k)
+    q1, q2, gpca, mu2 = util.compute_pca(m1, m2, k)
+    assert isinstance(gpca, util.LocalPCA)
+    np.testing.assert_allclose(mu2, mu, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(gpca.singular_values_, pca.singular_values_, rtol=1e-9)
+    np.testing.assert_allclose(gpca.mean_, pca.mean_, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(np.vstack([q1, q2]), np.vstack([p1, p2]), rtol=0, atol=1e-7)
+    want = wot_oracle.compute_default_cost_matrix(p1, p2, np.diag(pca.singular_values_))
+    got = wot_oracle.compute_default_cost_matrix(q1, q2, np.diag(gpca.singular_values_))
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)

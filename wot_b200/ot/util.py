@@ -4,8 +4,9 @@
 run its randomized solver (always at atlas shapes: max(shape) > 500 and k < 0.8 min(shape)) the same arithmetic
 runs on the GPU (csrc/pca.cu, float64): same centring, same Gaussian test matrix (numpy RandomState(58951)), same
 number of power iterations, same sign convention, so the components equal scikit-learn's to roundoff
-(tests: cost matrices agree to 1e-9).  Tiny problems, for which scikit-learn itself switches to an exact LAPACK
-solver, stay on scikit-learn.
+(tests: cost matrices agree to 1e-9).  Tiny or near-full-rank problems, for which scikit-learn itself switches to an
+exact LAPACK solver, and rank-deficient input take the exact GPU path (compute_pca_gpu_exact: Gram matrix of the short
+side, symmetric eigendecomposition, float64 on the device).  scikit-learn is never called by the product path.
 """
 from __future__ import annotations
 
@@ -102,31 +103,93 @@ def compute_pca_gpu(m1, m2, n_components, ctx=None):
     return comp[:n1], comp[n1:], pca, gene_means
 
 
+EXACT_MAX_SIDE = 8192          # largest Gram matrix of the exact path (float64: 0.5 GB)
+
+
+def compute_pca_gpu_exact(m1, m2, n_components, device=None):
+    """Exact-solver path of util.py:240-255 on the GPU, for the shapes where scikit-learn's PCA(svd_solver='auto') does
+    not run its randomized solver (few cells, or k close to the rank: `covariance_eigh` / `full`) and for
+    rank-deficient input.  Everything stays in float64 on the device: centring, the Gram matrix of the SHORT side of
+    the transposed matrix (library DGEMM through torch), its symmetric eigendecomposition (cuSOLVER through
+    torch.linalg.eigh), the other side's vectors by one more product.  scikit-learn's sign convention
+    (svd_flip(u_based_decision=False)) is applied, so components equal its LAPACK result up to roundoff wherever the
+    spectrum is non-degenerate.  There is no CPU path: without a CUDA device this raises."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.WotB200Error("local PCA needs a CUDA device (there is no CPU fallback)")
+    dev = torch.device("cuda", _lib.context().device if device is None else int(device))
+    a = torch.from_numpy(np.ascontiguousarray(_dense(m1), dtype=np.float64)).to(dev)
+    b = torch.from_numpy(np.ascontiguousarray(_dense(m2), dtype=np.float64)).to(dev)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("m1 and m2 must be 2-D with the same number of genes")
+    n1, n2, genes = a.shape[0], b.shape[0], a.shape[1]
+    cells = n1 + n2
+    k = min(int(n_components), cells)                        # util.py:247
+    if k > min(cells, genes):
+        raise ValueError("n_components=%d must be between 0 and min(n_samples, n_features)=%d" % (k, min(cells, genes)))
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    stacked = torch.cat([a, b], dim=0)                       # [cells, genes]
+    gene_means = stacked.mean(dim=0)
+    stacked = stacked - gene_means                           # util.py:244-246
+    cell_means = stacked.mean(dim=1)                         # sklearn centres the transposed matrix by feature = cell
+    xc = stacked - cell_means[:, None]                       # xc.T is the centred [genes, cells] matrix PCA factorises
+    if min(cells, genes) > EXACT_MAX_SIDE:
+        raise ValueError("exact local PCA: the short side (%d) exceeds %d" % (min(cells, genes), EXACT_MAX_SIDE))
+    if cells <= genes:
+        gram = xc @ xc.T                                     # [cells, cells] = V S^2 V^T
+        lam, vec = torch.linalg.eigh(gram)
+        lam, vec = lam.flip(0)[:k].clamp_min(0.0), vec.flip(1)[:, :k]
+        comp = vec                                           # [cells, k]: right singular vectors of xc.T
+    else:
+        gram = xc.T @ xc                                     # [genes, genes] = U S^2 U^T
+        lam, vec = torch.linalg.eigh(gram)
+        lam, vec = lam.flip(0)[:k].clamp_min(0.0), vec.flip(1)[:, :k]
+        comp = xc @ vec                                      # V = X^T U / S; |X^T u| = s, normalised directly so that
+        nrm = comp.norm(dim=0)                               # directions of (numerically) zero singular values stay finite
+        comp = comp / torch.where(nrm > 0, nrm, torch.ones_like(nrm))
+    sv = lam.sqrt()
+    top = comp.abs().argmax(dim=0)
+    sign = torch.sign(comp[top, torch.arange(k, device=dev)])
+    comp = comp * torch.where(sign == 0, torch.ones_like(sign), sign)
+    stop.record()
+    stop.synchronize()
+    comp_h = comp.cpu().numpy()
+    pca = LocalPCA(np.ascontiguousarray(comp_h.T), sv.cpu().numpy(), genes, cell_means.cpu().numpy(),
+                   start.elapsed_time(stop))
+    return comp_h[:n1], comp_h[n1:], pca, gene_means.cpu().numpy()
+
+
 def compute_pca(m1, m2, n_components, backend="auto"):
     """Joint PCA of two cell populations, fitted on the TRANSPOSED, gene-mean-centred matrix.
 
     Returns (pca_1 [I, n], pca_2 [J, n], fitted PCA, gene means), like util.py:240-255.
-    backend: 'auto' (GPU where scikit-learn would use its randomized solver), 'gpu', 'sklearn'."""
-    if backend not in ("auto", "gpu", "sklearn"):
-        raise ValueError("backend must be 'auto', 'gpu' or 'sklearn'")
+    backend: 'auto' -- always on the GPU: the randomized solver (csrc/pca.cu) where scikit-learn's svd_solver='auto'
+    would run its randomized solver, the exact solver (compute_pca_gpu_exact) for the small / near-full-rank shapes
+    where scikit-learn itself switches to LAPACK and for rank-deficient input; 'gpu' = the randomized solver,
+    'gpu_exact' = the exact one, 'sklearn' = the reference's own call (comparisons and tests only)."""
+    if backend not in ("auto", "gpu", "gpu_exact", "sklearn"):
+        raise ValueError("backend must be 'auto', 'gpu', 'gpu_exact' or 'sklearn'")
     n1, n2 = m1.shape[0], m2.shape[0]
     genes = m1.shape[1]
     k = min(int(n_components), n1 + n2)
     auto = backend == "auto"
     if auto:
         fits = k + N_OVERSAMPLES <= min(64, genes, n1 + n2)
-        backend = "gpu" if fits and sklearn_solver_choice(genes, n1 + n2, k) == "randomized" else "sklearn"
+        backend = "gpu" if fits and sklearn_solver_choice(genes, n1 + n2, k) == "randomized" else "gpu_exact"
     if backend == "sklearn":
         return compute_pca_sklearn(m1, m2, n_components)
+    if backend == "gpu_exact":
+        return compute_pca_gpu_exact(m1, m2, n_components)
     try:
         return compute_pca_gpu(m1, m2, n_components)
     except ValueError as exc:
         # numerically rank-deficient input (fewer independent cells or genes than k + 10 test vectors): the
-        # Cholesky-QR of the range finder has no positive pivot.  scikit-learn's LU/QR complete such a basis
-        # arbitrarily; that case is left to it rather than imitated.
+        # Cholesky-QR of the range finder has no positive pivot; the exact solver has no such requirement (the
+        # components that belong to zero singular values are arbitrary there, as they are in scikit-learn)
         if auto and "not positive definite" in str(exc):
-            logging.getLogger("wot").warning("local PCA: rank-deficient input, using scikit-learn (%s)", exc)
-            return compute_pca_sklearn(m1, m2, n_components)
+            logging.getLogger("wot").warning("local PCA: rank-deficient input, using the exact GPU solver (%s)", exc)
+            return compute_pca_gpu_exact(m1, m2, n_components)
         raise
 
 
