@@ -830,7 +830,7 @@ def test_gpu_pca_rank_deficient_input_takes_the_exact_gpu_solver(caplog):
 
 
 @pytest.mark.parametrize("cells,genes,k,solver", [([60, 70], 2000, 30, "covariance_eigh"), ([100, 120], 400, 30, "full"),
-                                                  ([15, 18], 600, 30, "full"), ([300, 350], 36, 30, "full"),
+                                                  ([15, 18], 200, 30, "full"), ([15, 18], 600, 30, "covariance_eigh"), ([300, 350], 36, 30, "full"),
                                                   ([400, 500], 9500, 30, "covariance_eigh")])
 def test_gpu_pca_exact_solver_shapes_vs_sklearn(cells, genes, k, solver):
     """The shapes where scikit-learn's svd_solver='auto' leaves its randomized solver (few cells: covariance_eigh; tiny

@@ -63,7 +63,7 @@ def main():
     names = {0: "simt", 1: "tcgen05 ew4", 2: "tcgen05 ew8", 3: "tcgen05 precise"}
     for dbg in range(1, 64):
         for base in (1, 2, 3):
-            names[base + 16 * dbg] = names[base] + "".join(t for b, t in ((1, " no-mma"), (2, " no-exp"), (8, " prof"), (16, " mma-x2"), (32, " no-accwait")) if dbg & b)
+            names[base + 16 * dbg] = names[base] + "".join(t for b, t in ((1, " no-mma"), (2, " no-exp"), (4, " ld-only"), (8, " prof"), (16, " mma-x2"), (32, " no-accwait")) if dbg & b)
     peak = C.c_double()
     _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak)))
     print("MUFU.EX2 peak (measured): %.3f T ex2/s" % (peak.value / 1e12), flush=True)

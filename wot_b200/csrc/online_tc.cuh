@@ -367,6 +367,21 @@ __host__ __device__ constexpr bool tc_pair_on_fma(int pair) {
          : ((pair + 1) * kTcFmaPairs / 8) != (pair * kTcFmaPairs / 8);
 }
 
+// measurement only (PROF build, dbg bit2): the 32 values as they come out of TMEM, summed with 16 FADD2 -- what the
+// epilogue costs when the exponentials are free.  Measured on B200 (profiles/r3c_tc_ld_only.txt): 1081 clocks per
+// 256 x 128 unit, bound by the MMA warps' issue chain; TMEM is read at >= 121 B/clk and is NOT what limits the pass.
+__device__ __forceinline__ float tc_plain_sum32(const uint32_t (&v)[32]) {
+    f32x2 s0 = 0ull, s1 = 0ull;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+        s0 = fadd2(s0, pack2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+        s1 = fadd2(s1, pack2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+    }
+    float lo, hi;
+    unpack2(fadd2(s0, s1), lo, hi);
+    return lo + hi;
+}
+
 __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
     f32x2 s0 = 0ull, s1 = 0ull;  // (0.f, 0.f)
 #pragma unroll
@@ -396,7 +411,8 @@ struct TcArgs {
     int n_stages;         // B ring depth
     double *part;         // [slots][out_ld] partial sums, one slot per (CTA that contributes to an out block, column half)
     unsigned int *counters;  // kTcRowBlocks * 4 per out block: one per group of 32 rows (tc_publish)
-    int dbg;              // measurement only: bit0 skip the MMAs, bit1 skip the exp2 work, bit3 write cycle counters
+    int dbg;              // measurement only: bit0 skip the MMAs, bit1 skip the epilogue work, bit2 TMEM loads + plain sums
+                          // (no exponentials), bit3 write cycle counters
     long long *prof;      // [CTA][epilogue warp][4]: cycles total, waiting for accumulators, waiting for tcgen05.ld, tiles
 };
 
@@ -706,6 +722,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
         const int rb = ew / EW, within = ew % EW;
         const int q = within & 3, h = within >> 2;
         const bool skip_exp = PROF && (A.dbg & 2) != 0;
+        const bool ld_only = PROF && (A.dbg & 4) != 0;
         const bool prof = PROF && (A.dbg & 8) != 0;
         long long c_acc = 0, c_ld = 0, c_t0 = PROF ? clock64() : 0, c_x = 0, c_pro = 0, c_fin = 0;
 #define TC_T0() if (PROF && prof) c_x = clock64()
@@ -754,7 +771,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                     WOTB_TMEM_WAIT32(va);  // chunk c (issued one step earlier)
                     TC_T1(c_ld);
                     WOTB_TMEM_LD32(vb, taddr + (c + 1) * 32);
-                    tile_sum += tc_exp2_sum32(va);
+                    tile_sum += (PROF && ld_only) ? tc_plain_sum32(va) : tc_exp2_sum32(va);
                     TC_T0();
                     WOTB_TMEM_WAIT32(vb);
                     TC_T1(c_ld);
@@ -775,7 +792,7 @@ __global__ void __launch_bounds__(128 + kTcRowBlocks * EW * 32, 1)
                             WOTB_TMEM_LD32(va, t_buf0 + nb * kTcAccCols);
                         }
                     }
-                    tile_sum += tc_exp2_sum32(vb);
+                    tile_sum += (PROF && ld_only) ? tc_plain_sum32(vb) : tc_exp2_sum32(vb);
                 }
                 facc += tile_sum;
             }
