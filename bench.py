@@ -7,7 +7,7 @@ compute_all_transport_maps: 39 day-pairs, 5-20k cells per day (seed 1), 30 local
 defaults eps=0.05 lambda1=1 lambda2=50, growth_iters=3.  A STEP is one day-pair transport map:
 median-normalised cost + 3 cold-start duality-gap solves + coupling and growth row sums.  Steps walk the
 39 pairs in order; with N GPUs rank r takes pair (step*N + r) mod 39 ("independent day-pairs shard one
-per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.  Every GPU keeps `--streams` (2)
+per GPU", no data-path collective), so per-GPU work is fixed: weak scaling.  Every GPU keeps `--streams` (3)
 day-pairs in flight on separate CUDA streams (wot_b200.pipeline; a step is still one day-pair).
 
   value  tmaps/s with every pair's coordinates already in HBM, timed with CUDA events on the library's
@@ -581,7 +581,7 @@ def run_ours(args, rank, world, local_rank):
     from wot_b200.pipeline import Pipeline
     # measured on B200 (profiles/r1h): two online solves in flight 7.28 tmaps/s vs 6.50 serial, three 6.66; the
     # stored kernel's cooperative launches do not interleave (4.82 vs 5.19), so it runs one at a time
-    n_streams = max(1, args.streams) if args.streams else (2 if args.kernel != "stored" else 1)
+    n_streams = max(1, args.streams) if args.streams else (3 if args.kernel != "stored" else 1)
     tstreams = [torch.cuda.Stream() for _ in range(n_streams)]
     pipe = Pipeline(local_rank, n_streams, make_stream=lambda k: tstreams[k].cuda_stream)
     ctx = pipe.contexts[0]

@@ -1338,6 +1338,19 @@ int online_rowsums(wotb_ctx *ctx, const double *x_out, int64_t n_out, const doub
             if ((double)hp[w] > tmax) tmax = (double)hp[w];
             ++warps;
         }
+        if (getenv("WOTB_TC_PROF_CTAS")) {  // per-CTA view: mean total / publish+finish cycles of its epilogue warps, units
+            fprintf(stderr, "[tc prof] per CTA: total fin units\n");
+            for (int c = 0; c < grid_used; ++c) {
+                double t = 0, f = 0, u = 0;
+                int nw = 0;
+                for (int w = 0; w < 16; ++w) {
+                    const size_t at = ((size_t)c * 16 + w) * 8;
+                    if (hp[at + 3] <= 0) continue;
+                    t += hp[at], f += hp[at + 5], u += hp[at + 3], ++nw;
+                }
+                if (nw) fprintf(stderr, "%d %.0f %.0f %.1f\n", c, t / nw, f / nw, u / nw);
+            }
+        }
         if (warps)
             fprintf(stderr,
                     "[tc prof] warps %zu units/warp %.1f | cycles per warp: total %.0f (max %.0f) = prologue %.0f + publish/finish "

@@ -54,7 +54,7 @@ class OTModel:
     **kwargs
         config, cell_filter, gene_filter, cell_day_filter, ncounts, ncells, solver, parameters, and any
         OT parameter (epsilon, lambda1, lambda2, growth_iters, local_pca, ...).
-        Additive (not in the reference): `streams` (default 2) = day-pairs compute_all_transport_maps keeps in
+        Additive (not in the reference): `streams` (default 3) = day-pairs compute_all_transport_maps keeps in
         flight on the GPU (wot_b200.pipeline; 1 = the reference's serial loop), `kernel` = 'auto' | 'stored' |
         'online'.
     """
@@ -71,7 +71,7 @@ class OTModel:
         day_filter = kwargs.pop("cell_day_filter", None)
         ncounts = kwargs.pop("ncounts", None)
         ncells = kwargs.pop("ncells", None)
-        self.streams = int(kwargs.pop("streams", 2))
+        self.streams = int(kwargs.pop("streams", 3))
         self.matrix = _io.filter_adata(self.matrix, obs_filter=cell_filter, var_filter=gene_filter)
         if day_filter is not None:
             keep_days = [float(t) for t in day_filter.split(",")] if isinstance(day_filter, str) else day_filter
