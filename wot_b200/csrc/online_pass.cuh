@@ -161,6 +161,8 @@ __device__ __forceinline__ void peer_store_col_partial(const PeerX &X, int o, do
     for (int w = 0; w < X.world; ++w) reinterpret_cast<double *>(X.buf[w] + X.off_t[p])[(long long)X.rank * X.ld_t + o] = s;
 }
 
+constexpr double kLog2e = 1.4426950408889634074;
+
 // What a finished out entry does with its reduced sum s (shared by the SIMT and the tcgen05 pass kernels).
 // Returns |a| or |b| for the tau test of a half-step, 0 otherwise.
 template <bool COLPASS>
@@ -170,20 +172,25 @@ __device__ __forceinline__ double online_apply(int mode, int o, double s, const 
     const int cur = ctrl->cur;
     double vmax = 0.0;
     if (mode == 0) {
+        // a = exp(z) with z = alpha (log mass - log s) + log damp (scaling_update); log2(a) is z log2(e), taken from z
+        // instead of from the rounded a: log s -> z -> {a, offset} is two transcendentals deep instead of four (this
+        // code is the tail of every pass for the CTA that draws the last ticket, profiles/r3d)
         if (!COLPASS) {
-            const double a = scaling_update(V.lp[o], s, ctrl->alpha1, V.lu[o]);
+            const double z = fma(ctrl->alpha1, V.lp[o] - log(s), V.lu[o]);
+            const double a = exp(z);
             V.a[cur ^ 1][o] = a;
             V.s[o] = s;
             if (ctrl->batch_done == 0) V.sfirst[o] = s;
-            V.Pd[o] = (ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + log2(a) - log2((double)I));
+            V.Pd[o] = (ctrl->c1 * V.u[o] - ctrl->c2 * V.nx[o] + z * kLog2e - ctrl->log2_I);
             if (V.tcXB) tc_store_in_offset(V.tcXB, o, V.Pd[o], V.tc_kseg, V.tc_nseg);
             if (V.peer) peer_store_row(*V.peer, o, a, s);
             vmax = fabs(a);
         } else {
-            const double b = scaling_update(ctrl->lq, s, ctrl->alpha2, V.lv[o]);
+            const double z = fma(ctrl->alpha2, ctrl->lq - log(s), V.lv[o]);
+            const double b = exp(z);
             V.b[cur ^ 1][o] = b;
             V.t[o] = s;
-            V.Qd[o] = (ctrl->c1 * V.v[o] - ctrl->c2 * V.ny[o] + log2(b) - log2((double)J));
+            V.Qd[o] = (ctrl->c1 * V.v[o] - ctrl->c2 * V.ny[o] + z * kLog2e - ctrl->log2_J);
             if (V.tcYB) tc_store_in_offset(V.tcYB, o, V.Qd[o], V.tc_kseg, V.tc_nseg);
             vmax = fabs(b);
         }

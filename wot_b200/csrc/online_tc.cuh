@@ -156,7 +156,7 @@ __global__ void k_tc_pack(const double *__restrict__ x, int n, int d, long long 
 }
 
 // Exponent offsets into the spare K slots: the out side's static offsets into its A-role rows (+ the
-// float64 residual), the in side's current offsets into its B-role rows.  During the iterations the in-side
+// float64 residual, stored as the factor 2^residual), the in side's current offsets into its B-role rows.  During the iterations the in-side
 // slots are kept current by the finishing code (tc_store_in_offset); this kernel runs when everything changed.
 __global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half *__restrict__ opA_out,
                            double *__restrict__ resid, const double *__restrict__ off_in, int n_in,
@@ -176,13 +176,13 @@ __global__ void k_tc_slots(const double *__restrict__ off_out, int n_out, __half
         if (nseg == 3) {
             __half a1, a2;
             tc_split(al, a1, a2);
-            resid[i] = al - (double)__half2float(a1) - (double)__half2float(a2) * (double)kTcLoInv;
+            resid[i] = exp2(al - (double)__half2float(a1) - (double)__half2float(a2) * (double)kTcLoInv);
             opA_out[tc_index(i, kseg - 1, kc)] = a1;
             opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
         } else {
             __half a1, a2, a3;
             // the residual is applied to the finished sum in float64 and is not subject to the accumulator's truncation
-            resid[i] = tc_split3(fmax(al * (1.0 + kTcTruncComp), (double)kTcPad), a1, a2, a3) / (1.0 + kTcTruncComp);
+            resid[i] = exp2(tc_split3(fmax(al * (1.0 + kTcTruncComp), (double)kTcPad), a1, a2, a3) / (1.0 + kTcTruncComp));
             opA_out[tc_index(i, kseg - 1, kc)] = a1;
             opA_out[tc_index(i, 2 * kseg - 1, kc)] = a2;
             opA_out[tc_index(i, 3 * kseg - 1, kc)] = a3;
@@ -401,7 +401,7 @@ __device__ __forceinline__ float tc_exp2_sum32(const uint32_t (&v)[32]) {
 struct TcArgs {
     const __half *opA;    // out side, A role (UMMA layout, rows padded to kTcOut)
     const __half *opB;    // in side, B role (rows padded to kTcOut)
-    const double *resid;  // out side: float64 residual of the static offsets
+    const double *resid;  // out side: 2^(float64 residual of the static offsets), the factor of the finished sum
     int out_n;            // valid out entries
     long long out_ld;     // stride of the partial-sum slots (>= padded out rows)
     int n_blocks;         // out blocks (256 rows) of this launch
@@ -509,7 +509,7 @@ __device__ __forceinline__ void tc_publish(const TcArgs &A, const SolveVecs &V, 
             if (H == 2) t += __ldcg(p + A.out_ld);
             sum += t;
         }
-        sum *= exp2(A.resid[row]);
+        sum *= A.resid[row];  // 2^residual, evaluated when the slots were written: one transcendental less in the tail
         vmax = online_apply<COLPASS>(mode, (int)row, sum, V, ctrl, rowsum_out);
         // persistent batch kernel: the offset slots just written are read by other CTAs' TMA loads after the grid barrier
         if (async_fence) asm volatile("fence.proxy.async.global;" ::: "memory");

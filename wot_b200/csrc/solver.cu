@@ -851,6 +851,8 @@ int init_ctrl(const wotb_params *prm, int64_t I, int64_t J, SolveCtrl *h, double
     h->primal = h->dual = NAN;
     h->need_build = 1;
     h->out_scale = 1.0 / (double)J;
+    h->log2_I = ::log2((double)I);
+    h->log2_J = ::log2((double)J);
     const bool tau_none = prm->tau != prm->tau;
     double eps;
     if (prm->solver == WOTB_SOLVER_DUALITY_GAP) {

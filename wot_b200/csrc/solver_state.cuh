@@ -55,6 +55,7 @@ struct SolveCtrl {
     // ---- online kernel only --------------------------------------------------------------------
     double inv_median;  // 1 / np.median(raw squared distances), ot_model.py:252
     double c1, c2;      // log2(e)/eps and log2(e)/(eps*median): exponents are formed in base 2
+    double log2_I, log2_J;  // constants of the offsets Pd / Qd
 };
 
 // ---- row-sharded solves exchanging over peer memory (NVLink / NVSwitch), see online_solve.cuh ------------------
