@@ -572,7 +572,12 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dist = None
+    bound_cpus = 0
     if world > 1:
+        # one process per GPU: keep this rank's threads and page-locked buffers on the GPU's NUMA node (at N = 1 the
+        # cpu_baseline leg wants every host core, so the process stays unbound)
+        from wot_b200.parallel import bind_host_to_gpu
+        bound_cpus = bind_host_to_gpu(local_rank)
         import torch.distributed as dist
         # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (set on the GPU boxes) prints a banner there
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -872,7 +877,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "tmaps/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * t_e2e / args.steps,
-                "contexts": n_e2e, "compute_slots": n_streams if n_e2e > n_streams else 0},
+                "contexts": n_e2e, "compute_slots": n_streams if n_e2e > n_streams else 0,
+                "host_cpus_bound_to_gpu": bound_cpus},
         "gpu_launches": int(launches),
         "roofline": roofline,
         other[0]: other[1],
