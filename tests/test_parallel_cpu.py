@@ -157,3 +157,97 @@ def test_parameter_sweep_two_ranks_matches_serial(tmp_path):
             np.testing.assert_array_equal(got["rowsum"], want["rowsum"])
         ran[per_rank[0][k]["rank"]] += 1
     assert sum(ran) == len(grid) and min(ran) >= 1          # both ranks drew from the queue
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side plumbing of the row-sharded solve (wot_b200.parallel.DistComm / ThreadComm)
+# ---------------------------------------------------------------------------------------------------
+def test_thread_comm_gathers_in_rank_order_and_synchronises():
+    """ThreadComm: the ranks are threads of one process; all_gather_object returns every rank's object in rank
+    order on every rank, twice in a row (the slots are reusable), barrier() is a rendezvous."""
+    import threading
+    from wot_b200.parallel import ThreadComm
+    world = 3
+    comms = ThreadComm.make(world)
+    out, order = [None] * world, []
+
+    def run(r):
+        c = comms[r]
+        assert (c.rank, c.world, c.in_process) == (r, world, True)
+        first = c.all_gather_object(("ptr", r * 100))
+        second = c.all_gather_object(None if r != 1 else "err")
+        order.append(r)
+        c.barrier()
+        assert len(order) == world                      # nobody passes the barrier before everybody arrived
+        out[r] = (first, second)
+        with pytest.raises(RuntimeError):
+            c.all_reduce(None)
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    for r in range(world):
+        assert out[r] == ([("ptr", 0), ("ptr", 100), ("ptr", 200)], [None, "err", None])
+
+
+def test_row_slices_tile_the_rows_in_256_row_blocks():
+    """hi_rows(n, rank, world): the rows of the slice of 256-row blocks a rank owns (the split wotb_online_open makes);
+    the slices tile [0, n) for every world size, empty slices included."""
+    from wot_b200.parallel import hi_rows
+    for n in (1, 255, 256, 257, 3000, 100000):
+        for world in (1, 2, 3, 8):
+            sizes = [hi_rows(n, r, world) for r in range(world)]
+            assert sum(sizes) == n and all(s >= 0 for s in sizes)
+            assert all(s % 256 == 0 for s in sizes[:-1] if s) or sum(1 for s in sizes if s % 256) <= 1
+
+
+def _comm_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import pickle
+
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wot_b200.parallel import DistComm
+        c = DistComm()
+        got = c.all_gather_object((None, bytes([rank]) * 64))     # what _PeerBuffers exchanges: (error, IPC handle)
+        t = torch.full((5,), float(rank + 1), dtype=torch.float64)
+        c.all_reduce(t)
+        c.barrier()
+        pickle.dump((c.rank, c.world, c.in_process, got, t.tolist()), open(os.path.join(out_dir, "comm_%d.pkl" % rank), "wb"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_dist_comm_two_ranks_gloo(tmp_path):
+    """DistComm over a gloo process group of two ranks: rank / world, the object gather of the 64-byte handles in
+    rank order, the SUM all-reduce of the nccl exchange."""
+    import pickle
+
+    import torch.multiprocessing as mp
+    mp.spawn(_comm_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        rank, world, in_process, got, summed = pickle.load(open(tmp_path / ("comm_%d.pkl" % r), "rb"))
+        assert (rank, world, in_process) == (r, 2, False)
+        assert got == [(None, b"\x00" * 64), (None, b"\x01" * 64)]
+        assert summed == [3.0] * 5
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml_device(monkeypatch):
+    """bind_host_to_gpu never raises: without a usable NVML device (or with WOTB_NO_NUMA_BIND=1) it reports 0 CPUs
+    bound and leaves the affinity alone."""
+    from wot_b200 import parallel
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("WOTB_NO_NUMA_BIND", "1")
+    assert parallel.bind_host_to_gpu(0) == 0
+    monkeypatch.delenv("WOTB_NO_NUMA_BIND")
+    n = parallel.bind_host_to_gpu(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
