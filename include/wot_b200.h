@@ -244,7 +244,9 @@ int wotb_online_open(wotb_ctx *ctx, const double *x0, int64_t I, const double *x
                      const double *G, const wotb_params *params, int32_t shard, int32_t n_shards, double *f, double *g,
                      void **solve);
 int wotb_online_step(void *solve, int32_t op, double *exchange);
-int wotb_online_state(void *solve, wotb_info *info, int32_t *done);
+int wotb_online_state(void *solve, wotb_info *info, int32_t *done);   /* synchronises the context's stream */
+int wotb_online_done(void *solve, int32_t *done);                      /* non-blocking: the done flag k_check raises in
+                                                                          mapped page-locked memory (keep batches in flight) */
 int wotb_online_rows(void *solve, int64_t *row_lo, int64_t *row_hi);
 void wotb_online_close(void *solve);
 

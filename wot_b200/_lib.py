@@ -85,6 +85,7 @@ SIGNATURES = {
                                    C.POINTER(_P)]),
     "wotb_online_step": (C.c_int, [_P, _I32, _P]),
     "wotb_online_state": (C.c_int, [_P, C.POINTER(Info), C.POINTER(_I32)]),
+    "wotb_online_done": (C.c_int, [_P, C.POINTER(_I32)]),
     "wotb_online_rows": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "wotb_online_close": (None, [_P]),
     "wotb_peer_alloc": (C.c_int, [_P, _I64, C.POINTER(_P), _P]),

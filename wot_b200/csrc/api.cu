@@ -92,6 +92,7 @@ int online_state(OnlineSolve *, wotb_info *, int *);
 void online_rows(OnlineSolve *, int64_t *, int64_t *);
 void online_close(OnlineSolve *);
 int64_t online_peer_bytes_of(OnlineSolve *, int);
+int online_done_flag(OnlineSolve *, int *);
 int online_attach(OnlineSolve *, int, void *const *);
 int sinkhorn_online(wotb_ctx *, const double *, int64_t, const double *, int64_t, int, double, const double *,
                     const wotb_params *, double *, double *, double *, wotb_info *);
@@ -633,6 +634,13 @@ int wotb_online_step(void *solve, int32_t op, double *exchange) { return online_
 int wotb_online_state(void *solve, wotb_info *info, int32_t *done) {
     int d = 0;
     const int rc = online_state((OnlineSolve *)solve, info, &d);
+    if (done) *done = d;
+    return rc;
+}
+
+int wotb_online_done(void *solve, int32_t *done) {
+    int d = 0;
+    const int rc = online_done_flag((OnlineSolve *)solve, &d);
     if (done) *done = d;
     return rc;
 }

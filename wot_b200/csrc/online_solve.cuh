@@ -707,6 +707,14 @@ int online_step(OnlineSolve *S, int op, double *exch) {
     return WOTB_OK;
 }
 
+// Non-blocking: has the device state machine raised its done flag (mapped page-locked memory, written by k_check)?
+// Lets the caller keep several batches in flight instead of synchronising on every one (online_state does).
+int online_done(OnlineSolve *S, int *done) {
+    WOTB_REQUIRE(S && done, "NULL argument");
+    *done = *reinterpret_cast<volatile int *>(S->ctx->status.as<int>()) != 0;
+    return WOTB_OK;
+}
+
 int online_state(OnlineSolve *S, wotb_info *info, int *done) {
     WOTB_REQUIRE(S && info && done, "NULL argument");
     WOTB_CUDA(cudaMemcpyAsync(&S->h, S->d_ctrl, sizeof(S->h), cudaMemcpyDeviceToHost, S->ctx->stream));

@@ -1203,6 +1203,7 @@ void online_close(OnlineSolve *S) {
     }
     delete S;
 }
+int online_done_flag(OnlineSolve *S, int *done) { return online_done(S, done); }
 int64_t online_peer_bytes_of(OnlineSolve *S, int world) { return (int64_t)online_peer_bytes(S->I, S->J, world); }
 int online_attach(OnlineSolve *S, int world, void *const *bufs) { return online_attach_peers(S, world, bufs); }
 }  // namespace wotb

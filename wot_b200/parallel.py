@@ -565,6 +565,26 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
                     batch()
+            if graph is not None and peers is not None and not finished:
+                # peer exchange: nothing in the graph is a collective, and every kernel of a batch that is not due is
+                # a no-op on the device -- so the ranks need not replay the same number of batches, and the host can
+                # keep `depth` batches in flight and look at the done flag (mapped page-locked memory) instead of
+                # synchronising on every batch.  (With NCCL inside the graph every rank must issue the same replays.)
+                depth = 3
+                ring = [torch.cuda.Event() for _ in range(depth)]
+                flag = C.c_int32(0)
+                k = 0
+                while True:
+                    graph.replay()
+                    ring[k % depth].record(stream)
+                    k += 1
+                    if k >= depth:
+                        ring[k % depth].synchronize()              # the oldest batch in flight
+                        _lib.check(lib.wotb_online_done(solve, C.byref(flag)))
+                        if flag.value:
+                            break
+                stream.synchronize()
+                finished = state()
             while not finished:
                 if graph is not None:
                     graph.replay()
