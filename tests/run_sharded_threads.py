@@ -20,7 +20,10 @@ def main():
 
     n0, n1, world = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
     eps = float(sys.argv[4]) if len(sys.argv) > 4 else 0.05
+    fixed = len(sys.argv) > 5 and sys.argv[5] == "stablev2"      # the fixed-iteration solver (optimal_transport.py:167-236)
     params = dict(DEFAULTS, epsilon=eps)
+    if fixed:
+        params.update(scaling_iter=330, extra_iter=40, inner_iter_max=50, solver=_lib.SOLVER_FIXED_ITERS)
     torch.cuda.set_device(0)
     x0, x1, growth = synthetic.day_pair_coords(n0, n1, d=30, seed=321)
     ctx = _lib.Context(0)
@@ -55,8 +58,12 @@ def main():
         sys.exit(1)
     one = parallel.sharded_online_solve(x0, x1, growth, device=0, median=med.value, **params)
     info = orc.SolveInfo()
-    want = orc.optimal_transport_duality_gap(C=orc.compute_default_cost_matrix(x0, x1), G=growth, info=info,
-                                             gap="marginal", **params)
+    cost = orc.compute_default_cost_matrix(x0, x1)
+    if fixed:
+        oparams = {k: v for k, v in params.items() if k != "solver"}
+        want = orc.transport_stablev2(C=cost, G=growth, info=info, **oparams)
+    else:
+        want = orc.optimal_transport_duality_gap(C=cost, G=growth, info=info, gap="marginal", **params)
     ok = True
     covered = 0
     for r, res in enumerate(results):
@@ -69,7 +76,8 @@ def main():
         same = (res["info"]["batches"] == one["info"]["batches"] and res["info"]["iters"] == one["info"]["iters"])
         d1 = float(np.max(np.abs(res["f"].cpu().numpy() - one["f"].cpu().numpy()))) / eps
         good = (err <= 1e-4 and ferr <= 1e-4 and rerr <= 1e-4 and same and d1 <= 1e-5
-                and abs(res["info"]["batches"][5] - info.batches[5]) <= 1)
+                and (fixed or abs(res["info"]["batches"][5] - info.batches[5]) <= 1)
+                and (not fixed or res["info"]["iters"] == info.iters))
         ok = ok and good
         print("rank %d/%d rows [%d,%d) coupling err %.2e f err %.2e rowsum err %.2e vs one rank %.1e batches %s vs %s %s"
               % (r, world, lo, hi, err, ferr, rerr, d1, res["info"]["batches"], info.batches, "OK" if good else "FAIL"),

@@ -18,8 +18,9 @@ def test_stepping_path_single_gpu(eps):
     assert "OK" in out.stdout
 
 
-@pytest.mark.parametrize("world,eps", [(2, "0.05"), (3, "0.05"), (2, "0.01")])
-def test_peer_memory_exchange_in_process_ranks(world, eps):
+@pytest.mark.parametrize("world,eps,solver", [(2, "0.05", "duality_gap"), (3, "0.05", "duality_gap"), (2, "0.01", "duality_gap"),
+                                              (2, "0.05", "stablev2")])
+def test_peer_memory_exchange_in_process_ranks(world, eps, solver):
     """The peer-memory exchange (stores from the passes' finishing code into every rank's buffer, flag barrier,
     rank-ordered sums; no collective) with the ranks as threads of one process on ONE GPU: oracle parity, identical
     bits on every rank, identical batch counts to the one-rank solve."""
@@ -27,7 +28,7 @@ def test_peer_memory_exchange_in_process_ranks(world, eps):
     # ANOTHER rank that waits for this rank's flag, so the host waits for every flag kernel (online_solve.cuh)
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", WOTB_PEER_HOST_SYNC="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_sharded_threads.py"), "1500", "1637",
-                          str(world), eps], capture_output=True, text=True, timeout=900, env=env)
+                          str(world), eps, solver], capture_output=True, text=True, timeout=900, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "ALL OK" in out.stdout
 
