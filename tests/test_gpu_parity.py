@@ -196,11 +196,11 @@ def test_otmodel_default_path_vs_reference(ot, golden):
 
 @pytest.mark.parametrize("fuse", [True, False])
 @pytest.mark.parametrize("shape", [(1500, 1637), (2000, 2000), (997, 4099), (4100, 513), (300, 19000), (130, 23040),
-                                   (200, 24001), (150, 30011), (301, 47000)])
+                                   (200, 24001), (150, 30011), (301, 47000), (70, 95000)])
 def test_default_solver_vs_oracle_from_coords(ot, shape, fuse):
     """Config 1 scale: GPU default cost + STORED-kernel solver from coordinates against the float64 oracle.  fuse=True:
     K read once per iteration -- one CTA per row up to 23,040 columns (k_fused), a thread-block cluster per row beyond
-    (k_fused_cl: 24,001 -> 2 CTAs, 47,000 -> 4); fuse=False: the two-sweep kernels."""
+    (k_fused_cl: 24,001 -> 2 CTAs, 47,000 -> 4, 95,000 -> 8); fuse=False: the two-sweep kernels."""
     from oracle import wot_oracle as orc
     from wot_b200 import synthetic
     n0, n1 = shape
