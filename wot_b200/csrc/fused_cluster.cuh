@@ -171,12 +171,19 @@ __global__ void __launch_bounds__(kFuseThreads, 1)
                 double part_sum = lane < kFclComputeWarps ? red[s * 32 + lane] : 0.0;
                 part_sum = warp_sum(part_sum);
                 if (lane < CL) {
-                    // lane l hands the partial to CTA l of the cluster (itself included)
+                    // lane l hands the partial to CTA l of the cluster; the own CTA's copy goes through plain shared-memory
+                    // forms (same barrier, same release), which is also what compute-sanitizer's racecheck can follow
                     const int x = (int)(kk % kFclSlots);
-                    const uint32_t slot = mapa_shared(smem_u32(&xsum[x * kFuseMaxCluster + cr]), (uint32_t)lane);
-                    const uint32_t bar = mapa_shared(smem_u32(&xready[x]), (uint32_t)lane);
-                    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(slot), "d"(part_sum) : "memory");
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+                    if (lane == cr) {
+                        xsum[x * kFuseMaxCluster + cr] = part_sum;
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&xready[x]))
+                                     : "memory");
+                    } else {
+                        const uint32_t slot = mapa_shared(smem_u32(&xsum[x * kFuseMaxCluster + cr]), (uint32_t)lane);
+                        const uint32_t bar = mapa_shared(smem_u32(&xready[x]), (uint32_t)lane);
+                        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(slot), "d"(part_sum) : "memory");
+                        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+                    }
                 }
                 __syncwarp();
             }
