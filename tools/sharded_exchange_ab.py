@@ -34,19 +34,23 @@ def main():
     med = first["median"]
     parallel.sharded_online_solve(x0, x1, growth, exchange="peer", median=med, **prm)  # mappings, warm-up
     times = {"nccl": [], "peer": []}
+    caps = {"nccl": [], "peer": []}
     for rep in range(reps):
         for mode in ("nccl", "peer"):
             tm = {}
             res = parallel.sharded_online_solve(x0, x1, growth, exchange=mode, median=med, timers=tm, **prm)
-            t = torch.tensor([res["info"]["gpu_ms"]], dtype=torch.float64, device="cuda")
+            t = torch.tensor([res["info"]["gpu_ms"], res["info"]["graph_capture_ms"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            times[mode].append(float(t.item()))
+            times[mode].append(float(t[0].item()))
+            caps[mode].append(float(t[1].item()))
             if rank == 0:
-                print("rep %d %-4s %.1f ms  iters %d batches %s (%s)" % (rep, mode, times[mode][-1], res["info"]["iters"],
-                                                                     res["info"]["batches"], tm.get("exchange")), flush=True)
+                print("rep %d %-4s %.1f ms (of which graph capture on the host %.1f ms)  iters %d batches %s (%s)"
+                      % (rep, mode, times[mode][-1], caps[mode][-1], res["info"]["iters"], res["info"]["batches"],
+                         tm.get("exchange")), flush=True)
     if rank == 0:
         print(json.dumps({"shape": [n, n], "n_gpus": world, "host_cpus_bound_to_gpu": bound,
                           "nccl_ms": times["nccl"], "peer_ms": times["peer"],
+                          "nccl_capture_ms": caps["nccl"], "peer_capture_ms": caps["peer"],
                           "nccl_median_ms": float(np.median(times["nccl"])), "peer_median_ms": float(np.median(times["peer"]))}),
               flush=True)
     dist.destroy_process_group()

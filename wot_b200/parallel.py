@@ -17,6 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import threading
+import time
 
 import numpy as np
 
@@ -561,10 +562,15 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
             ev[0].record(stream)
             batch()                               # first batch eagerly: sizes the lazily grown workspaces
             finished = state()
+            capture_ms = 0.0
             if use_graph and not finished:
+                # host-side work with the GPU idle (stream capture + graph instantiation; with NCCL inside the graph it
+                # also registers the collective's buffers): part of gpu_ms, reported separately as graph_capture_ms
+                t_cap = time.perf_counter()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
                     batch()
+                capture_ms = 1e3 * (time.perf_counter() - t_cap)
             if graph is not None and peers is not None and not finished:
                 # peer exchange: nothing in the graph is a collective, and every kernel of a batch that is not due is
                 # a no-op on the device -- so the ranks need not replay the same number of batches, and the host can
@@ -626,6 +632,7 @@ def sharded_online_solve(x0, x1, G, group=None, device=None, stream=None, timers
             lib.wotb_online_close(solve)
         out_info = info.as_dict()
         out_info["gpu_ms"] = ev[0].elapsed_time(ev[1])
+        out_info["graph_capture_ms"] = capture_ms
         out_info["median_ms"] = median_ms
     return {"f": f, "g": g, "rowsum": rowsum, "rows": (lo.value, hi.value), "median": median, "info": out_info,
             "ctx": ctx, "coords": (X0, X1), "stream": stream}
