@@ -29,8 +29,9 @@ day-pairs in flight on separate CUDA streams (wot_b200.pipeline; a step is still
   e2e_api       the same workload through the PUBLIC model API from expression matrices:
                 OTModel(adata, growth_iters=3).compute_all_transport_maps -> local PCA on the GPU, cost, solves,
                 .h5ad files (first --api-pairs day-pairs).
-  row_sharded   N > 1: BASELINE.json configs[3], one 100k x 100k pair with its rows sharded over the N GPUs and an
-                NCCL all-reduce per Sinkhorn iteration; timing, all-reduce share and parity checks.
+  row_sharded   N > 1: BASELINE.json configs[3], one 100k x 100k pair with its rows sharded over the N GPUs; the ranks
+                exchange from inside the pass kernels over peer memory (headline) or with one NCCL all-reduce per Sinkhorn
+                iteration (timed beside it); timings, parity checks against the one-GPU solve and float64 marginals.
 
 `--impl reference` times the reference's own CPU implementation of the path on the host cores: cost
 (sklearn pairwise_distances + np.median, ot_model.py:249-252) + compute_transport_matrix(optimal_transport_duality_gap,
@@ -597,8 +598,8 @@ def run_ours(args, rank, world, local_rank):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from wot_b200.pipeline import Pipeline
-    # measured on B200 (profiles/r1h): two online solves in flight 7.28 tmaps/s vs 6.50 serial, three 6.66; the
-    # stored kernel's cooperative launches do not interleave (4.82 vs 5.19), so it runs one at a time
+    # measured on B200 (profiles/r3e_streams.txt): online solves in flight 2 -> 8.19-8.33, 3 -> 8.53, 4 -> 8.57 tmaps/s;
+    # the stored kernel's cooperative launches do not interleave (round 1: 4.82 vs 5.19), so it runs one at a time
     n_streams = max(1, args.streams) if args.streams else (3 if args.kernel != "stored" else 1)
     tstreams = [torch.cuda.Stream() for _ in range(n_streams)]
     pipe = Pipeline(local_rank, n_streams, make_stream=lambda k: tstreams[k].cuda_stream)
@@ -779,7 +780,7 @@ def run_ours(args, rank, world, local_rank):
     _lib.check(ctx.lib.wotb_bench_mufu_dev(ctx.handle, C.byref(peak_c)))
     mufu_peak = peak_c.value / 1e12
 
-    # ---- configs[3] on N > 1 GPUs: one 100k x 100k pair, rows sharded, NCCL all-reduce per iteration ----
+    # ---- configs[3] on N > 1 GPUs: one 100k x 100k pair, rows sharded, peer-memory exchange (and NCCL beside it) ----
     row_sharded = None
     if world > 1 and not args.no_extras:
         for c in pipe.contexts:
