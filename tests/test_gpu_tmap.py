@@ -174,3 +174,34 @@ def test_glue_and_interpolate(chain):
         assert same.mean() >= 0.995, same.mean()
     with pytest.raises(TypeError):
         interpolate_with_ot(e0, e1, T01, 0.5, 10)
+
+
+def test_model_from_directory_equals_implicit_model(tmp_path):
+    """Files written by OTModel.compute_all_transport_maps (default '.h5ad') read back through
+    ImplicitTransportMapModel.from_directory (the consumer side of the layout, transport_map_model.py:652-732): same
+    meta table, and trajectories / fates equal those of the model built on the implicit couplings of the same solves."""
+    from wot_b200 import ot, synthetic
+    from wot_b200._anndata import AnnData
+    from wot_b200.tmap import ImplicitTransportMapModel, StoredTransportMap
+    X, day, growth = synthetic.expression_matrix([210, 260, 190], n_genes=120, seed=21)
+    obs = pd.DataFrame({"day": day, "cell_growth_rate": growth}, index=["c%d" % i for i in range(len(day))])
+    model = ot.OTModel(AnnData(X, obs, pd.DataFrame(index=["g%d" % i for i in range(X.shape[1])])), growth_iters=2,
+                       local_pca=15)
+    model.compute_all_transport_maps(tmap_out=str(tmp_path / "tm"))
+    stored = ImplicitTransportMapModel.from_directory(str(tmp_path / "tm"))
+    implicit = ImplicitTransportMapModel.from_ot_model(model)
+    assert stored.timepoints == implicit.timepoints == [0.0, 1.0, 2.0]
+    assert list(stored.meta.index) == list(implicit.meta.index) and list(stored.meta["day"]) == list(implicit.meta["day"])
+    assert all(isinstance(m, StoredTransportMap) for m in stored.tmaps.values())
+    assert list(stored.tmaps[(0.0, 1.0)].obs.columns) == ["g0", "g1", "g2"]
+    day1 = list(obs.index[day == 1.0])
+    pops_s = stored.population_from_ids(day1[:50], day1[50:140], at_time=1.0, names=["A", "B"])
+    pops_i = implicit.population_from_ids(day1[:50], day1[50:140], at_time=1.0, names=["A", "B"])
+    np.testing.assert_allclose(stored.trajectories(pops_s).values, implicit.trajectories(pops_i).values, rtol=5 * RTOL)
+    np.testing.assert_allclose(stored.fates(pops_s).values, implicit.fates(pops_i).values, rtol=5 * RTOL, atol=1e-12)
+    StoredTransportMap.resident = 1                      # the second map evicts the first: results must not change
+    try:
+        np.testing.assert_allclose(stored.trajectories(pops_s).values, implicit.trajectories(pops_i).values, rtol=5 * RTOL)
+    finally:
+        StoredTransportMap.resident = 2
+        StoredTransportMap._cache.clear()

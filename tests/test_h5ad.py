@@ -122,3 +122,41 @@ def test_anndata_write_and_async_writer(tmp_path):
     with pytest.raises(OSError):
         with h5ad.AsyncWriter() as w:
             w.submit(lambda: wio.write_dataset(ad, str(tmp_path / "no_such_dir" / "x"), output_format="h5ad"))
+
+
+def test_model_from_directory_of_written_maps(tmp_path):
+    """The consumer side of the output layout (transport_map_model.py:652-732): a directory of '{prefix}_{t0}_{t1}.h5ad'
+    files written here becomes a model with the reference's meta table (every cell id with its day), the maps opened
+    lazily with ids only; unrelated files and other prefixes are ignored; an empty match raises like the reference."""
+    import numpy as np
+    import pandas as pd
+
+    from wot_b200 import _lib
+    from wot_b200 import h5ad as h5
+    from wot_b200.tmap import ImplicitTransportMapModel, StoredTransportMap
+    rng = np.random.default_rng(3)
+    sizes = [5, 7, 4]
+    ids = [["d%d_%d" % (k, i) for i in range(n)] for k, n in enumerate(sizes)]
+    mats = {}
+    for k, (t0, t1) in enumerate([(0.0, 1.5), (1.5, 2.0)]):
+        X = rng.random((sizes[k], sizes[k + 1]))
+        mats[(t0, t1)] = X
+        h5.write_h5ad(str(tmp_path / ("tm_%s_%s.h5ad" % (t0, t1))), X, ids[k], [("g0", np.ones(sizes[k]))], ids[k + 1])
+    (tmp_path / "tm_g.txt").write_text("id\tg0\n")
+    h5.write_h5ad(str(tmp_path / "other_0.0_1.5.h5ad"), mats[(0.0, 1.5)], ids[0], [], ids[1])
+    model = ImplicitTransportMapModel.from_directory(str(tmp_path / "tm"))
+    assert model.timepoints == [0.0, 1.5, 2.0] and sorted(model.tmaps) == [(0.0, 1.5), (1.5, 2.0)]
+    assert list(model.meta.index) == sum(ids, []) and list(model.meta["day"]) == [0.0] * 5 + [1.5] * 7 + [2.0] * 4
+    m = model.tmaps[(0.0, 1.5)]
+    assert isinstance(m, StoredTransportMap) and m.shape == (5, 7) and list(m.obs.columns) == ["g0"]
+    pops = model.population_from_ids(ids[1][:3], at_time=1.5, names=["A"])
+    assert pops[0].p.sum() == 3
+    import torch
+    if torch.cuda.is_available():
+        got = model.pull_back(*pops, normalize=False)
+        np.testing.assert_allclose(got.p, mats[(0.0, 1.5)] @ pops[0].p, rtol=1e-13)
+    else:
+        with pytest.raises(_lib.WotB200Error, match="no CPU fallback"):
+            model.pull_back(*pops)
+    with pytest.raises(ValueError, match="No transport maps found"):
+        ImplicitTransportMapModel.from_directory(str(tmp_path / "nothing"))

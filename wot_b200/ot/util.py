@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import threading
 
 import numpy as np
 import scipy.sparse
@@ -104,6 +105,16 @@ def compute_pca_gpu(m1, m2, n_components, ctx=None):
 
 
 EXACT_MAX_SIDE = 8192          # largest Gram matrix of the exact path (float64: 0.5 GB)
+_EIGH_LOCK = threading.Lock()
+
+
+def _eigh(gram):
+    """torch.linalg.eigh behind a lock: torch loads its CUDA linear-algebra backend lazily on the first call, and that
+    loader must not run in two threads at once ("lazy wrapper should be called at most once" when the workers of
+    wot_b200.pipeline hit their first small local PCA together)."""
+    import torch
+    with _EIGH_LOCK:
+        return torch.linalg.eigh(gram)
 
 
 def compute_pca_gpu_exact(m1, m2, n_components, device=None):
@@ -138,12 +149,12 @@ def compute_pca_gpu_exact(m1, m2, n_components, device=None):
         raise ValueError("exact local PCA: the short side (%d) exceeds %d" % (min(cells, genes), EXACT_MAX_SIDE))
     if cells <= genes:
         gram = xc @ xc.T                                     # [cells, cells] = V S^2 V^T
-        lam, vec = torch.linalg.eigh(gram)
+        lam, vec = _eigh(gram)
         lam, vec = lam.flip(0)[:k].clamp_min(0.0), vec.flip(1)[:, :k]
         comp = vec                                           # [cells, k]: right singular vectors of xc.T
     else:
         gram = xc.T @ xc                                     # [genes, genes] = U S^2 U^T
-        lam, vec = torch.linalg.eigh(gram)
+        lam, vec = _eigh(gram)
         lam, vec = lam.flip(0)[:k].clamp_min(0.0), vec.flip(1)[:, :k]
         comp = xc @ vec                                      # V = X^T U / S; |X^T u| = s, normalised directly so that
         nrm = comp.norm(dim=0)                               # directions of (numerically) zero singular values stay finite

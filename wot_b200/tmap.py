@@ -10,7 +10,9 @@ neither the 3.2 GB dense coupling nor its trip over PCIe.
 
 `ImplicitTransportMapModel` chains such maps over consecutive day-pairs with the reference's semantics:
 push_forward / pull_back with `to_time` and per-step normalisation (:235-365), trajectories (:105-143), fates
-(:40-69), transition_table (:71-103), and glue (wot/tmap/util.py:74-94) as composition.
+(:40-69), transition_table (:71-103), and glue (wot/tmap/util.py:74-94) as composition.  The same model can be built
+from a directory of written transport-map files (`ImplicitTransportMapModel.from_directory`, `StoredTransportMap`): the
+consumer side of the `.h5ad` output layout (:652-732).
 """
 from __future__ import annotations
 
@@ -117,6 +119,85 @@ class ImplicitTransportMap:
         return out.cpu().numpy()
 
 
+class StoredTransportMap:
+    """A transport map that lives in a FILE written by compute_all_transport_maps ('{prefix}_{t0}_{t1}.h5ad' / .npz),
+    with the interface of ImplicitTransportMap: the consumer side of the output layout
+    (TransportMapModel.from_directory reads such files, wot/tmap/transport_map_model.py:652-732, and multiplies
+    populations with them at :290 and :356).  The cell ids are read when the object is made (for .h5ad without touching
+    /X); the I x J matrix is read and moved to the GPU on first use and a small number of matrices is kept there
+    (`StoredTransportMap.resident`, least recently used first out).  Products are float64 library GEMMs on the device;
+    there is no CPU path."""
+
+    resident = 2          # matrices kept on the GPU at a time
+    _cache = []           # [(map, device tensor)], most recently used last
+
+    def __init__(self, path, t0=None, t1=None):
+        from . import io as _io
+        self.path, self.t0, self.t1 = str(path), t0, t1
+        if self.path.lower().endswith(".h5ad") and not _io.HAVE_ANNDATA:
+            from . import h5ad
+            d = h5ad.read_h5ad(self.path, with_x=False)
+            self.obs = pd.DataFrame({k: v for k, v in d["obs"].items()}, index=pd.Index(d["obs_index"].astype(str)))
+            self.var = pd.DataFrame(index=pd.Index(d["var_index"].astype(str)))
+        else:
+            ds = _io.read_dataset(self.path)
+            self.obs, self.var = ds.obs, ds.var
+        self._shape = (len(self.obs), len(self.var))
+
+    @property
+    def shape(self):
+        return self._shape
+
+    def _matrix(self):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.WotB200Error("transport-map products need a CUDA device (there is no CPU fallback)")
+        cache = StoredTransportMap._cache
+        for k, (owner, t) in enumerate(cache):
+            if owner is self:
+                cache.append(cache.pop(k))
+                return t
+        from . import io as _io
+        X = np.ascontiguousarray(np.asarray(_io.read_dataset(self.path).X), dtype=np.float64)
+        if X.shape != self._shape:
+            raise ValueError("%s: matrix is %s, ids say %s" % (self.path, X.shape, self._shape))
+        while len(cache) >= max(1, StoredTransportMap.resident):
+            cache.pop(0)
+        t = torch.from_numpy(X).to(torch.device("cuda", _lib.context().device))
+        cache.append((self, t))
+        return t
+
+    def _apply(self, p, forward, normalize):
+        import torch
+        p = np.asarray(p, dtype=np.float64)
+        single = p.ndim == 1
+        p = np.ascontiguousarray(np.atleast_2d(p))
+        n_in = self._shape[0] if forward else self._shape[1]
+        if p.shape[1] != n_in:
+            raise ValueError("population has %d entries, the map has %d cells on that side" % (p.shape[1], n_in))
+        X = self._matrix()
+        pd_ = torch.from_numpy(p).to(X.device)
+        out = (pd_ @ X if forward else (X @ pd_.T).T).cpu().numpy()          # :290 / :356
+        if normalize:
+            out = (out.T / out.sum(axis=1)).T
+        return out[0] if single else out
+
+    def push_forward(self, p, normalize=False):
+        return self._apply(p, True, normalize)
+
+    def pull_back(self, p, normalize=False):
+        return self._apply(p, False, normalize)
+
+    def row_sums(self):
+        return self.pull_back(np.ones(self._shape[1]))
+
+    def col_sums(self):
+        return self.push_forward(np.ones(self._shape[0]))
+
+    def to_dense(self, device=None):
+        return self._matrix().cpu().numpy()
+
+
 class GluedTransportMap:
     """tmap_0 @ tmap_1 (glue_transport_maps, wot/tmap/util.py:74-94) for implicit maps: the product is never formed,
     populations go through the factors one after the other.  The cells of the intermediate day must be in the
@@ -192,6 +273,34 @@ class ImplicitTransportMapModel:
         t = ot_model.timepoints
         return cls({(t[k], t[k + 1]): ot_model.compute_implicit_transport_map(t[k], t[k + 1]) for k in range(len(t) - 1)},
                    timepoints=t)
+
+    @classmethod
+    def from_directory(cls, tmap_out, with_covariates=False):
+        """The model of a directory of transport-map files, as TransportMapModel.from_directory builds it
+        (transport_map_model.py:652-732): files '{prefix}_{t0}_{t1}.h5ad' (also .npz / .txt here) next to `tmap_out`'s
+        prefix, `meta` = every cell id with its day (rows of every map, columns of the last one), maps opened lazily
+        (StoredTransportMap).  ValueError when no file matches, like the reference."""
+        import os
+        import re
+        if with_covariates:
+            raise ValueError("covariate-split maps ('_cv{a}_cv{b}') are not chained into a model here")
+        tmap_dir, prefix = os.path.split(str(tmap_out))
+        tmap_dir, prefix = tmap_dir or ".", prefix or "tmaps"
+        day = r"([0-9]*\.?[0-9]+)"
+        pattern = re.compile(re.escape(prefix) + "_" + day + "_" + day + r"\.(h5ad|npz|txt)$")
+        found = {}
+        for name in sorted(os.listdir(tmap_dir)):
+            m = pattern.match(name)
+            path = os.path.join(tmap_dir, name)
+            if m is not None and os.path.isfile(path):
+                found[(float(m.group(1)), float(m.group(2)))] = path
+        if not found:
+            raise ValueError("No transport maps found in " + tmap_dir + " with prefix " + prefix)
+        keys = sorted(found)
+        tmaps = {k: StoredTransportMap(found[k], t0=k[0], t1=k[1]) for k in keys}
+        frames = [pd.DataFrame(index=tmaps[k].obs.index, data={"day": k[0]}) for k in keys]
+        frames.append(pd.DataFrame(index=tmaps[keys[-1]].var.index, data={"day": keys[-1][1]}))
+        return cls(tmaps, meta=pd.concat(frames), timepoints=sorted({t for k in keys for t in k}))
 
     # ---- populations ----------------------------------------------------------------------------------------
     def population_from_ids(self, *ids, at_time, names=None):
