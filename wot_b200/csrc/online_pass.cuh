@@ -168,7 +168,7 @@ constexpr double kLog2e = 1.4426950408889634074;
 template <bool COLPASS>
 __device__ __forceinline__ double online_apply(int mode, int o, double s, const SolveVecs &V, SolveCtrl *ctrl,
                                                double *rowsum_out) {
-    const int I = ctrl->I, J = ctrl->J;
+    const int J = ctrl->J;
     const int cur = ctrl->cur;
     double vmax = 0.0;
     if (mode == 0) {
