@@ -537,8 +537,9 @@ __device__ __forceinline__ void tc_publish(const TcArgs &A, const SolveVecs &V, 
 // grid in contiguous ranges (block-major), "stream-K" style: every SM gets the same number of units whatever
 // the shape, and the per-CTA fixed cost (TMEM allocation, barrier setup, pipeline fill) is paid once.  A CTA's
 // range may cross out-block boundaries; the A blocks are double buffered (3-segment operands) so the switch costs
-// nothing.  Each (out block, CTA) pair writes its partial row sums into its own slot; the last CTA to arrive at an
-// out block adds the slots in slot order and applies the update, so the result does not depend on timing.
+// nothing.  Every epilogue warp writes the partial sums of its 32 rows into its own slot and the warp that arrives
+// last at a (block, 32-row group) adds the slots in a fixed order and applies the update (tc_publish), so the result
+// does not depend on timing.
 //
 // modes as in k_online_pass: 0 half-step, 1 row sums for the gap, 2 coupling row sums, 3 S0 partials,
 // 4 partial sums only (row-sharded solves).  EW = epilogue warps per row block (4: thread = row x 128 columns,
