@@ -160,3 +160,24 @@ def test_model_from_directory_of_written_maps(tmp_path):
             model.pull_back(*pops)
     with pytest.raises(ValueError, match="No transport maps found"):
         ImplicitTransportMapModel.from_directory(str(tmp_path / "nothing"))
+
+
+def test_model_from_directory_reads_npz_maps_too(tmp_path):
+    """The 'npz' output format (usable without anndata / h5py) is read back by from_directory like the .h5ad files."""
+    import numpy as np
+    import pandas as pd
+
+    from wot_b200 import io as wio
+    from wot_b200._anndata import AnnData
+    from wot_b200.tmap import ImplicitTransportMapModel
+    rng = np.random.default_rng(5)
+    ids = [["a%d" % i for i in range(4)], ["b%d" % i for i in range(6)]]
+    X = rng.random((4, 6))
+    obs = pd.DataFrame({"g0": np.ones(4), "g1": np.arange(4.0)}, index=ids[0])
+    wio.write_dataset(AnnData(X, obs, pd.DataFrame(index=ids[1])), str(tmp_path / "maps_3_4.5"), output_format="npz")
+    model = ImplicitTransportMapModel.from_directory(str(tmp_path / "maps"))
+    assert model.timepoints == [3.0, 4.5]
+    m = model.tmaps[(3.0, 4.5)]
+    assert m.shape == (4, 6) and list(m.obs.index) == ids[0] and list(m.var.index) == ids[1]
+    assert list(m.obs.columns) == ["g0", "g1"]
+    assert list(model.meta["day"]) == [3.0] * 4 + [4.5] * 6
